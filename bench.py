@@ -1,0 +1,269 @@
+#!/usr/bin/env python
+"""bench.py — GiB/s of fused RS(12,4) encode + HighwayHash256 bitrot over 1 MiB blocks (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W          (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference ...                    (the CPU path on the host cores; rank 0 only)
+
+A step = one pass of the hot path over the resident synthetic stream (BASELINE config 2: 10 GiB of
+random object bytes per GPU -> 10240 erasure blocks; inputs are far larger than the 126 MB L2, so no
+explicit flush is needed).  `value` is device-resident (inputs already in HBM); `e2e` goes through the
+host-buffer C-ABI call (pinned host memory, H2D + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K, M, BS = 12, 4, 1 << 20
+S = -(-BS // K)                      # 87382
+ALGO_BYTES_PER_BLOCK = BS + M * S + (K + M) * 32   # 1 398 616
+GiB = float(1 << 30)
+METRIC = "fused RS(12,4) encode + HighwayHash256 bitrot, 1 MiB blocks"
+
+
+def read_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(nblocks, reps, threads):
+    """The reference's two-pass CPU path (SIMD RS encode, then HighwayHash of every shard) on host cores."""
+    import oracle_lib as o
+    o.build()
+    L = o.lib()
+    rng = np.random.default_rng(0x4D494E494F00 + 2)
+    src = rng.integers(0, 256, nblocks * BS, dtype=np.uint8)
+    parity = np.zeros(nblocks * M * S, dtype=np.uint8)
+    dig = np.zeros(nblocks * (K + M) * 32, dtype=np.uint8)
+    L.orc_encode_hash_blocks_mt(K, M, BS, src.ctypes.data, min(nblocks, 16), parity.ctypes.data, dig.ctypes.data, threads, 1)  # warm
+    sec = L.orc_encode_hash_blocks_mt(K, M, BS, src.ctypes.data, nblocks, parity.ctypes.data, dig.ctypes.data, threads, reps)
+    return nblocks * reps * BS / GiB / sec, sec, L.orc_simd_level().decode()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blocks", type=int, default=10240, help="erasure blocks per GPU per step (10240 = 10 GiB)")
+    ap.add_argument("--e2e-blocks", type=int, default=2048)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        nb = 512  # 512 MiB sample per step
+        vals = []
+        gib, sec, lvl = cpu_reference_run(nb, 1, threads)  # warm-up
+        for _ in range(max(args.warmup - 1, 0)):
+            cpu_reference_run(nb, 1, threads)
+        t0 = time.time()
+        for _ in range(args.steps):
+            g, s, lvl = cpu_reference_run(nb, 1, threads)
+            vals.append(s)
+        ms = 1e3 * sum(vals) / len(vals)
+        value = nb * BS / GiB / (sum(vals) / len(vals))
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "GiB/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": "RS(12,4) encode+HighwayHash256S bitrot, 1 MiB blocks", "sample": f"{nb} MiB per step"},
+            "cpu_baseline": {"value": value, "unit": "GiB/s", "cores": threads, "kind": "port",
+                             "sample": f"{nb} x 1 MiB blocks per step, C oracle ({lvl}) with {threads} pthreads; Go toolchain absent"},
+            "e2e": {"value": value, "unit": "GiB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import minio_b200 as mb
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    nblocks = args.blocks
+    nbytes = nblocks * BS
+    pitch = (S + 15) // 16 * 16
+
+    # synthetic object stream, generated on device (counter-based Philox via torch), seed per BASELINE.md §4
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(0x4D494E494F00 + 2 + rank)
+    src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    step = 1 << 30
+    for o0 in range(0, nbytes, step):
+        n = min(step, nbytes - o0)
+        src[o0:o0 + n] = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=gen)
+    par = torch.empty((nblocks * M, pitch), dtype=torch.uint8, device=dev)
+    dig = torch.empty((nblocks, K + M, 32), dtype=torch.uint8, device=dev)
+    codec = mb.Codec(K, M, BS, device=local)
+    stream = torch.cuda.current_stream()
+
+    def one_step():
+        codec.encode_blocks_device(src.data_ptr(), nbytes, par.data_ptr(), pitch, dig.data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = codec.launches
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_all0 = torch.cuda.Event(enable_timing=True); t_all1 = torch.cuda.Event(enable_timing=True)
+    t_all0.record(stream)
+    for a, b in evs:
+        a.record(stream); one_step(); b.record(stream)
+    t_all1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = codec.launches - l0
+    total_ms = t_all0.elapsed_time(t_all1)
+    kern_ms = [a.elapsed_time(b) for a, b in evs]
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * nbytes / GiB / (ms_per_step / 1e3)
+
+    # ---- spot verification against the oracle (outside the timed region)
+    verified = None
+    if rank == 0:
+        import oracle_lib as o
+        o.build()
+        verified = True
+        for b in (0, nblocks // 2, nblocks - 1):
+            blk = src[b * BS:(b + 1) * BS].cpu().numpy()
+            sh = o.encode_data(K, M, blk, fast=True)
+            hp = par[b * M:(b + 1) * M, :S].cpu().numpy()
+            hd = dig[b].cpu().numpy()
+            for j in range(M):
+                verified &= bool(np.array_equal(hp[j], sh[K + j]))
+            for i in range(K + M):
+                verified &= hd[i].tobytes() == o.hh256(sh[i], fast=True)
+
+    # ---- e2e: host pinned buffers through the C ABI (H2D + kernel + D2H per step)
+    e2e = None
+    if not args.no_e2e:
+        eb = min(args.e2e_blocks, nblocks)
+        h_src = torch.empty(eb * BS, dtype=torch.uint8).pin_memory()
+        h_src.copy_(src[:eb * BS])
+        h_par = torch.empty(eb * M * S, dtype=torch.uint8).pin_memory()
+        h_dig = torch.empty(eb * (K + M) * 32, dtype=torch.uint8).pin_memory()
+        L = mb.lib()
+        def e2e_step():
+            rc = L.mec_encode_blocks(codec.h, h_src.data_ptr(), eb * BS, h_par.data_ptr(), h_dig.data_ptr())
+            assert rc == 0, rc
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * eb * BS * args.steps / GiB / dt, "unit": "GiB/s", "h2d_bytes_per_step": eb * BS,
+               "d2h_bytes_per_step": eb * (M * S + (K + M) * 32), "sample": f"{eb} blocks per step per GPU, pinned host buffers"}
+        if rank == 0 and verified:
+            b = eb - 1
+            sh = o.encode_data(K, M, h_src[b * BS:(b + 1) * BS].numpy(), fast=True)
+            verified &= bool(np.array_equal(h_par.numpy()[(b * M) * S:(b * M + 1) * S], sh[K]))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = read_peaks()
+    kavg_ms = sum(kern_ms) / len(kern_ms)
+    achieved = ALGO_BYTES_PER_BLOCK * nblocks / (kavg_ms / 1e3) / 1e9
+    out = {
+        "metric": METRIC, "value": value, "unit": "GiB/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+        "data": "synthetic",
+        "config": {"workload": f"BASELINE config 2: RS(12,4) encode+HighwayHash256S bitrot, 1 MiB blocks, {nblocks} blocks "
+                               f"({nbytes / GiB:.2f} GiB stream) per GPU, device-resident",
+                   "l2": "inputs (>=10 GiB per step) exceed the 126 MB L2; no explicit flush", "parallelism": f"sets-per-gpu x{world}"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_block": ALGO_BYTES_PER_BLOCK,
+                     "kernel_ms": kavg_ms, "blocks_per_launch": nblocks},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "verified_vs_oracle": verified,
+    }
+    if not args.no_cpu and world == 1:
+        nb = 256
+        gib, sec, lvl = cpu_reference_run(nb, max(1, int(12 / max(nb * BS / GiB / 8.0, 1e-3)) // 8), threads)
+        out["cpu_baseline"] = {"value": gib, "unit": "GiB/s", "cores": threads, "kind": "port",
+                               "sample": f"{nb} x 1 MiB blocks, {sec:.1f} s of C oracle ({lvl}) encode then hash, {threads} pthreads"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

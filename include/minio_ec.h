@@ -1,0 +1,142 @@
+/*
+ * minio_ec.h — C ABI of the B200 erasure-code + bitrot library (libminio_ec.so).
+ *
+ * Drop-in boundary for MinIO's erasure hot path.  The reference has no FFI here — the path sits
+ * behind Go interfaces (reedsolomon.Encoder held by `Erasure.encoder`, hash.Hash from
+ * BitrotAlgorithm.New, io.Writer / io.ReaderAt per drive).  Each entry point names the reference
+ * function whose body a cgo binding would replace (file:line under /root/reference); the Go-side
+ * stub is written out in INTEGRATION.md.  Plain pointers and sizes only; no retained caller memory.
+ *
+ * Return codes: 0 / non-negative = success, negative = one of MEC_ERR_*.
+ */
+#ifndef MINIO_EC_H
+#define MINIO_EC_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- errors: reedsolomon.Err* (go.mod:49) and MinIO storage errors ------------------------- */
+enum {
+  MEC_OK = 0,
+  MEC_ERR_INV_SHARD_NUM = -1,     /* reedsolomon.ErrInvShardNum   cmd/erasure-coding.go:45 */
+  MEC_ERR_MAX_SHARD_NUM = -2,     /* reedsolomon.ErrMaxShardNum   cmd/erasure-coding.go:49 */
+  MEC_ERR_TOO_FEW_SHARDS = -3,    /* reedsolomon.ErrTooFewShards */
+  MEC_ERR_SHARD_NO_DATA = -4,     /* reedsolomon.ErrShardNoData */
+  MEC_ERR_SHARD_SIZE = -5,        /* reedsolomon.ErrShardSize */
+  MEC_ERR_SHORT_DATA = -6,        /* reedsolomon.ErrShortData */
+  MEC_ERR_FILE_CORRUPT = -7,      /* errFileCorrupt        cmd/storage-errors.go:104 */
+  MEC_ERR_LESS_DATA = -8,         /* errLessData           cmd/storage-errors.go:114 */
+  MEC_ERR_UNEXPECTED = -9,        /* errUnexpected         cmd/storage-errors.go:29 */
+  MEC_ERR_READ_QUORUM = -10,      /* errErasureReadQuorum  cmd/erasure-errors.go:23 */
+  MEC_ERR_WRITE_QUORUM = -11,     /* errErasureWriteQuorum cmd/erasure-errors.go:26 */
+  MEC_ERR_INVALID_ARGUMENT = -12, /* errInvalidArgument */
+  MEC_ERR_CUDA = -100,            /* CUDA runtime / driver failure (see mec_last_error) */
+  MEC_ERR_NO_DEVICE = -101,       /* no CUDA device: the library never falls back to the CPU */
+  MEC_ERR_UNSUPPORTED = -102      /* geometry or algorithm outside the GPU path */
+};
+
+/* ---- bitrot algorithms: cmd/xl-storage-format-v1.go:142-159 -------------------------------- */
+enum { MEC_SHA256 = 1, MEC_HIGHWAYHASH256 = 2, MEC_HIGHWAYHASH256S = 3, MEC_BLAKE2B512 = 4 };
+
+typedef struct mec_codec mec_codec;
+
+/* ---- lifecycle ----------------------------------------------------------------------------- */
+/* NewErasure (cmd/erasure-coding.go:42): validates k>0, m>=0, k+m<=256 with the same errors.
+ * `device` is the CUDA ordinal.  One codec may be shared by threads; calls serialise per codec. */
+int mec_codec_new(int k, int m, int64_t block_size, int bitrot_algo, int device, mec_codec** out);
+void mec_codec_free(mec_codec* c);
+int mec_device_count(void);
+const char* mec_last_error(void); /* thread-local description of the last MEC_ERR_CUDA */
+const char* mec_version(void);
+
+/* ---- size helpers -------------------------------------------------------------------------- */
+int64_t mec_shard_size(const mec_codec* c);                                  /* Erasure.ShardSize       cmd/erasure-coding.go:116 */
+int64_t mec_shard_file_size(const mec_codec* c, int64_t total_length);       /* Erasure.ShardFileSize   cmd/erasure-coding.go:121 */
+int64_t mec_shard_file_offset(const mec_codec* c, int64_t start_offset, int64_t length,
+                              int64_t total_length);                         /* Erasure.ShardFileOffset cmd/erasure-coding.go:135 */
+int64_t mec_bitrot_shard_file_size(int64_t size, int64_t shard_size, int algo); /* bitrotShardFileSize cmd/bitrot.go:156 */
+int64_t mec_ceil_frac(int64_t numerator, int64_t denominator);               /* ceilFrac cmd/utils.go:689 */
+
+/* ---- pinned host memory for the byte pool (internal/bpool/bpool.go:52,68 AllocAligned) ------ */
+void* mec_alloc_pinned(size_t bytes);
+void mec_free_pinned(void* p);
+
+/* ---- fused block encode: the body of Erasure.EncodeData (cmd/erasure-coding.go:77-91) plus
+ * the HighwayHash256 of every shard that streamingBitrotWriter.Write computes
+ * (cmd/bitrot-streaming.go:57-59), for ALL erasure blocks of `src` in one call.
+ *   src      : len object bytes (host).  Blocks are block_size bytes; the last may be short.
+ *   parity   : receives parity shard j of block b at parity + (b*m + j)*shard_size  (host)
+ *   digests  : receives 32-byte digest of shard i of block b at digests + (b*(k+m)+i)*32 (host)
+ * Data shards alias `src` exactly as Split does (shard i of block b = src[b*block_size + i*S_b ..),
+ * zero padded), so they are not copied back.  len == 0 is a no-op (EncodeData returns nil shards). */
+int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* parity, uint8_t* digests);
+
+/* Same, device-resident: d_src/d_parity/d_digests are device pointers on the codec's device,
+ * d_src 16-byte aligned, parity row pitch `parity_pitch` (multiple of 16, >= shard_size):
+ * parity shard (b, j) at d_parity + (b*m + j)*parity_pitch.  Asynchronous on `cuda_stream`
+ * (a cudaStream_t, may be NULL). */
+int mec_encode_blocks_device(mec_codec* c, const uint8_t* d_src, int64_t len, uint8_t* d_parity,
+                             int64_t parity_pitch, uint8_t* d_digests, void* cuda_stream);
+
+/* ---- fused block reconstruct: Erasure.DecodeDataBlocks / DecodeDataAndParityBlocks
+ * (cmd/erasure-coding.go:94-113 -> reedsolomon ReconstructData / Reconstruct) fused with the
+ * digest check of streamingBitrotReader.ReadAt (cmd/bitrot-streaming.go:186-196).
+ *   frames[i]   : host pointer to shard file i in streaming-bitrot layout ([32B digest][shard])*,
+ *                 or NULL when the drive is offline.  All `nblocks` blocks are full blocks except
+ *                 that the last block's shard length is `last_shard_len` (0 => shard_size).
+ *   want[i]     : 1 = rebuild shard i into out[i] (same frame layout, digests recomputed)
+ *   data_only   : ReconstructData semantics (parity never rebuilt)
+ *   corrupt[i]  : set to 1 when any frame of file i fails its digest
+ * The first k readable files in index order are used (parallelReader.Read, cmd/erasure-decode.go:127);
+ * a file with a corrupt frame is dropped for the whole call and the next one is tried. */
+int mec_reconstruct_frames(mec_codec* c, const uint8_t* const* frames, int64_t nblocks,
+                           int64_t last_shard_len, const uint8_t* want, int data_only,
+                           uint8_t* const* out, uint8_t* corrupt);
+
+/* ---- whole-part drivers ------------------------------------------------------------------- */
+/* Erasure.Encode (cmd/erasure-encode.go:69) with one streaming bitrot writer per shard
+ * (cmd/bitrot.go:105, cmd/bitrot-streaming.go:44): files[i] (host, or NULL = offline writer)
+ * receives exactly the bytes of part.N on drive i; each must hold
+ * mec_bitrot_shard_file_size(mec_shard_file_size(len)) bytes.  Fails with MEC_ERR_WRITE_QUORUM
+ * when fewer than `write_quorum` writers are online.  Returns bytes consumed. */
+int64_t mec_encode(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, int write_quorum);
+
+/* Erasure.Decode (cmd/erasure-decode.go:239) over streaming bitrot readers: writes object bytes
+ * [offset, offset+length) of a part of `total_length` bytes to dst.  files[i] NULL = offline.
+ * Returns bytes written; *heal_hint is set to MEC_ERR_FILE_CORRUPT when a frame failed its digest
+ * but the read still succeeded (the errFileCorrupt side-band of cmd/erasure-decode.go:288-293). */
+int64_t mec_decode(mec_codec* c, const uint8_t* const* files, int64_t offset, int64_t length,
+                   int64_t total_length, uint8_t* dst, int* heal_hint);
+
+/* Erasure.Heal (cmd/erasure-decode.go:317): rebuilds every shard file with out_files[i] != NULL
+ * from the readable files (NULL = offline / stale). */
+int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total_length, uint8_t* const* out_files);
+
+/* bitrotVerify (cmd/bitrot.go:164) for the streaming algorithm: scans a whole shard file. */
+int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file_len, int64_t part_len);
+
+/* ---- shard-shaped low-level calls (keep Erasure.EncodeData / reedsolomon.Encoder shapes) ---- */
+/* reedsolomon.Encoder.Encode: shards[0..k) in, shards[k..k+m) out, each shard_len bytes (host). */
+int mec_rs_encode_shards(mec_codec* c, uint8_t* const* shards, int64_t shard_len);
+/* reedsolomon.Encoder.Reconstruct / ReconstructData: shards[i] with present[i]==0 are rebuilt in
+ * place (buffers must exist). */
+int mec_rs_reconstruct_shards(mec_codec* c, uint8_t* const* shards, const uint8_t* present,
+                              int64_t shard_len, int data_only);
+/* hash.Hash one-shot for BitrotAlgorithm.New() == HighwayHash256(S) (cmd/bitrot.go:55-58): digests
+ * of `count` equal-length messages laid out back to back (host). */
+int mec_hh256_batch(mec_codec* c, const uint8_t* msgs, int64_t msg_len, int64_t count, uint8_t* digests);
+
+/* erasureSelfTest + bitrotSelfTest (cmd/erasure-coding.go:149, cmd/bitrot.go:224) on the GPU. */
+int mec_selftest(int device);
+
+/* tuning knobs for benchmarks/tests (erasure blocks per CTA, loader, GF specialisation) */
+int mec_set_option(mec_codec* c, const char* name, int64_t value);
+/* number of kernels launched by this codec so far (bench.py's gpu_launches) */
+int64_t mec_launch_count(const mec_codec* c);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,228 @@
+"""ctypes binding of include/minio_ec.h.  Host buffers are numpy uint8 arrays; device buffers are
+raw pointers (e.g. ``torch.Tensor.data_ptr()``)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+SHA256, HIGHWAYHASH256, HIGHWAYHASH256S, BLAKE2B512 = 1, 2, 3, 4
+ERRORS = {-1: "ErrInvShardNum", -2: "ErrMaxShardNum", -3: "ErrTooFewShards", -4: "ErrShardNoData", -5: "ErrShardSize",
+          -6: "ErrShortData", -7: "errFileCorrupt", -8: "errLessData", -9: "errUnexpected", -10: "errErasureReadQuorum",
+          -11: "errErasureWriteQuorum", -12: "errInvalidArgument", -100: "CUDA error", -101: "no CUDA device",
+          -102: "unsupported on the GPU path"}
+
+_LIB = None
+
+
+class MecError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        detail = lib().mec_last_error().decode() if code <= -100 else ""
+        super().__init__(f"{what}: {ERRORS.get(code, code)} ({code}) {detail}")
+
+
+def lib_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libminio_ec.so")
+
+
+def lib():
+    """Load libminio_ec.so.  Fails loudly when the CUDA extension has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback)")
+    L = C.CDLL(path)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    L.mec_codec_new.argtypes = [i32, i32, i64, i32, i32, C.POINTER(vp)]
+    L.mec_codec_free.argtypes = [vp]
+    L.mec_codec_free.restype = None
+    L.mec_last_error.restype = C.c_char_p
+    L.mec_version.restype = C.c_char_p
+    for f, args in (("mec_shard_size", [vp]), ("mec_shard_file_size", [vp, i64]),
+                    ("mec_shard_file_offset", [vp, i64, i64, i64]), ("mec_bitrot_shard_file_size", [i64, i64, i32]),
+                    ("mec_ceil_frac", [i64, i64]), ("mec_launch_count", [vp])):
+        getattr(L, f).restype = i64
+        getattr(L, f).argtypes = args
+    L.mec_alloc_pinned.restype = vp
+    L.mec_alloc_pinned.argtypes = [C.c_size_t]
+    L.mec_free_pinned.argtypes = [vp]
+    L.mec_free_pinned.restype = None
+    L.mec_encode_blocks.argtypes = [vp, vp, i64, vp, vp]
+    L.mec_encode_blocks_device.argtypes = [vp, vp, i64, vp, i64, vp, vp]
+    L.mec_reconstruct_frames.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp]
+    L.mec_encode.restype = i64
+    L.mec_encode.argtypes = [vp, vp, i64, vp, i32]
+    L.mec_decode.restype = i64
+    L.mec_decode.argtypes = [vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
+    L.mec_heal.argtypes = [vp, vp, i64, vp]
+    L.mec_bitrot_verify.argtypes = [vp, vp, i64, i64]
+    L.mec_rs_encode_shards.argtypes = [vp, vp, i64]
+    L.mec_rs_reconstruct_shards.argtypes = [vp, vp, vp, i64, i32]
+    L.mec_hh256_batch.argtypes = [vp, vp, i64, i64, vp]
+    L.mec_selftest.argtypes = [i32]
+    L.mec_set_option.argtypes = [vp, C.c_char_p, i64]
+    _LIB = L
+    return L
+
+
+def device_count():
+    return lib().mec_device_count()
+
+
+def selftest(device=0):
+    rc = lib().mec_selftest(device)
+    if rc:
+        raise MecError(rc, "mec_selftest")
+
+
+def _u8(a):
+    if isinstance(a, (bytes, bytearray, memoryview)):
+        a = np.frombuffer(a, dtype=np.uint8)
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+def _ptrs(arrs):
+    return (C.c_void_p * len(arrs))(*[(a.ctypes.data if (a is not None and a.size) else None) for a in arrs])
+
+
+class Codec:
+    """NewErasure (cmd/erasure-coding.go:42) bound to one CUDA device."""
+
+    def __init__(self, k, m, block_size=1 << 20, algo=HIGHWAYHASH256S, device=0):
+        h = C.c_void_p()
+        rc = lib().mec_codec_new(k, m, block_size, algo, device, C.byref(h))
+        if rc:
+            raise MecError(rc, "mec_codec_new")
+        self.h, self.k, self.m, self.n, self.block_size, self.algo = h, k, m, k + m, block_size, algo
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mec_codec_free(self.h)
+            self.h = None
+
+    __del__ = close
+
+    # -- helpers
+    def set_option(self, name, value):
+        rc = lib().mec_set_option(self.h, name.encode(), int(value))
+        if rc:
+            raise MecError(rc, "mec_set_option")
+
+    @property
+    def launches(self):
+        return lib().mec_launch_count(self.h)
+
+    def shard_size(self):
+        return lib().mec_shard_size(self.h)
+
+    def shard_file_size(self, total):
+        return lib().mec_shard_file_size(self.h, total)
+
+    def shard_file_offset(self, start, length, total):
+        return lib().mec_shard_file_offset(self.h, start, length, total)
+
+    def bitrot_file_size(self, total):
+        return lib().mec_bitrot_shard_file_size(self.shard_file_size(total), self.shard_size(), self.algo)
+
+    # -- block level
+    def encode_blocks(self, src):
+        """-> (parity [nblocks, m, S], digests [nblocks, n, 32]); the last block may use < S bytes per row."""
+        src = _u8(src)
+        nb = -(-src.size // self.block_size)
+        S = self.shard_size()
+        parity = np.zeros((nb, max(self.m, 1), S), dtype=np.uint8)
+        dig = np.zeros((nb, self.n, 32), dtype=np.uint8)
+        rc = lib().mec_encode_blocks(self.h, src.ctypes.data if src.size else None, src.size, parity.ctypes.data, dig.ctypes.data)
+        if rc:
+            raise MecError(rc, "mec_encode_blocks")
+        return parity[:, :self.m], dig
+
+    def encode_blocks_device(self, d_src, length, d_parity, parity_pitch, d_digests, stream=0):
+        rc = lib().mec_encode_blocks_device(self.h, d_src, length, d_parity, parity_pitch, d_digests, stream)
+        if rc:
+            raise MecError(rc, "mec_encode_blocks_device")
+
+    # -- whole part
+    def encode(self, src, online=None, write_quorum=0):
+        src = _u8(src)
+        fsz = self.bitrot_file_size(src.size)
+        online = [True] * self.n if online is None else online
+        files = [np.zeros(fsz, dtype=np.uint8) if online[i] else None for i in range(self.n)]
+        rc = lib().mec_encode(self.h, src.ctypes.data if src.size else None, src.size, _ptrs(files), write_quorum)
+        if rc < 0:
+            raise MecError(rc, "mec_encode")
+        return files
+
+    def decode(self, files, offset, length, total):
+        files = [None if f is None else _u8(f) for f in files]
+        dst = np.zeros(max(length, 1), dtype=np.uint8)
+        hint = C.c_int(0)
+        rc = lib().mec_decode(self.h, _ptrs(files), offset, length, total, dst.ctypes.data, C.byref(hint))
+        if rc < 0:
+            raise MecError(rc, "mec_decode")
+        return dst[:length], hint.value
+
+    def heal(self, files, stale, total):
+        files = [None if f is None else _u8(f) for f in files]
+        fsz = self.bitrot_file_size(total)
+        outs = [np.zeros(fsz, dtype=np.uint8) if stale[i] else None for i in range(self.n)]
+        rc = lib().mec_heal(self.h, _ptrs(files), total, _ptrs(outs))
+        if rc:
+            raise MecError(rc, "mec_heal")
+        return outs
+
+    def reconstruct_frames(self, frames, nblocks, last_shard_len, want, data_only=False):
+        frames = [None if f is None else _u8(f) for f in frames]
+        S = self.shard_size()
+        last = last_shard_len or S
+        fbytes = (nblocks - 1) * (32 + S) + 32 + last if nblocks else 0
+        want = np.asarray(want, dtype=np.uint8)
+        outs = [np.zeros(fbytes, dtype=np.uint8) if want[i] else None for i in range(self.n)]
+        corrupt = np.zeros(self.n, dtype=np.uint8)
+        rc = lib().mec_reconstruct_frames(self.h, _ptrs(frames), nblocks, last_shard_len, want.ctypes.data,
+                                          1 if data_only else 0, _ptrs(outs), corrupt.ctypes.data)
+        if rc:
+            raise MecError(rc, "mec_reconstruct_frames")
+        return outs, corrupt
+
+    def bitrot_verify(self, file, part_len):
+        f = _u8(file)
+        return lib().mec_bitrot_verify(self.h, f.ctypes.data if f.size else None, f.size, part_len)
+
+    # -- shard shaped
+    def rs_encode_shards(self, shards):
+        """reedsolomon.Encoder.Encode: list of k+m equally sized arrays, parity written in place."""
+        per = shards[0].size
+        rc = lib().mec_rs_encode_shards(self.h, _ptrs(shards), per)
+        if rc:
+            raise MecError(rc, "mec_rs_encode_shards")
+
+    def rs_reconstruct_shards(self, shards, present, data_only=False):
+        per = max(s.size for s in shards)
+        pres = np.asarray(present, dtype=np.uint8)
+        return lib().mec_rs_reconstruct_shards(self.h, _ptrs(shards), pres.ctypes.data, per, 1 if data_only else 0)
+
+    def hh256_batch(self, msgs, msg_len, count):
+        msgs = _u8(msgs)
+        out = np.zeros((count, 32), dtype=np.uint8)
+        rc = lib().mec_hh256_batch(self.h, msgs.ctypes.data if msgs.size else None, msg_len, count, out.ctypes.data)
+        if rc:
+            raise MecError(rc, "mec_hh256_batch")
+        return out
+
+    def encode_data(self, data):
+        """Erasure.EncodeData (cmd/erasure-coding.go:77): Split + Encode -> k+m shard arrays."""
+        data = _u8(data)
+        if data.size == 0:
+            return [np.zeros(0, dtype=np.uint8) for _ in range(self.n)]
+        per = -(-data.size // self.k)
+        store = np.zeros(self.n * per, dtype=np.uint8)
+        store[:data.size] = data
+        shards = [store[i * per:(i + 1) * per] for i in range(self.n)]
+        if self.m:
+            self.rs_encode_shards(shards)
+        return shards

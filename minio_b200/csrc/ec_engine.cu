@@ -1,0 +1,216 @@
+// ec_engine.cu — kernel instantiation + dispatch for the fused RS + HighwayHash kernel.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include "../../include/minio_ec.h"
+#include "ec_engine.h"
+
+namespace mec {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& s) { g_last_error = s; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+int DevBuf::ensure(size_t n) {
+  if (n <= cap) return MEC_OK;
+  release();
+  size_t want = n + (n >> 3) + 256;
+  MEC_CUDA_OK(cudaMalloc(&p, want));
+  cap = want;
+  return MEC_OK;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+// (k, m) pairs with compile-time specialised GF code.  MinIO's default parity for a 16-drive set
+// is EC:4 => RS(12,4) (internal/config/storageclass/storage-class.go:355); the others are the
+// BASELINE configs and common set sizes.
+#define MEC_STATIC_CONFIGS(X) X(12, 4) X(4, 2) X(16, 4) X(8, 8) X(8, 4) X(6, 2) X(10, 4) X(14, 2) X(2, 2)
+
+using KernelFn = void (*)(const FusedParams, const TmaMaps);
+
+struct StaticEntry {
+  int k, m;
+  KernelFn tma, bytewise;
+};
+static const StaticEntry kStaticTable[] = {
+#define X(K, M) {K, M, fused_rs_hh_kernel<GfStatic<K, M>, true>, fused_rs_hh_kernel<GfStatic<K, M>, false>},
+    MEC_STATIC_CONFIGS(X)
+#undef X
+};
+
+Engine::Engine(int device) : device_(device) {}
+Engine::~Engine() {}
+
+int Engine::init() {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_last_error("no CUDA device available; this library has no CPU fallback");
+    return MEC_ERR_NO_DEVICE;
+  }
+  if (device_ < 0 || device_ >= count) return MEC_ERR_INVALID_ARGUMENT;
+  MEC_CUDA_OK(cudaSetDevice(device_));
+  cudaDeviceProp prop;
+  MEC_CUDA_OK(cudaGetDeviceProperties(&prop, device_));
+  num_sms_ = prop.multiProcessorCount;
+  if (prop.major < 10) {
+    set_last_error("device is not sm_100-class (kernels are built for sm_100a only)");
+    return MEC_ERR_UNSUPPORTED;
+  }
+  cudaDriverEntryPointQueryResult qres;
+  MEC_CUDA_OK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &encode_tiled_, cudaEnableDefault, &qres));
+  if (qres != cudaDriverEntryPointSuccess || !encode_tiled_) {
+    set_last_error("cuTensorMapEncodeTiled not available");
+    return MEC_ERR_CUDA;
+  }
+  return MEC_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_map(void* fn, CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1,
+                    uint32_t box0, uint32_t box1) {
+  cuuint64_t dims[2] = {dim0, dim1};
+  cuuint64_t strides[1] = {stride1};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base),
+                                                    dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(static_cast<int>(r)));
+    return MEC_ERR_CUDA;
+  }
+  return MEC_OK;
+}
+
+int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStream_t st) {
+  if (d.nblocks <= 0 || d.S < 0) return MEC_OK;
+  if (d.S == 0 && (d.r > 0 || d.digests == nullptr)) return MEC_OK;  // S == 0: digest of the empty message only
+  if (d.k <= 0 || d.k > kMaxK || d.r < 0 || d.r > kMaxR) return MEC_ERR_UNSUPPORTED;
+  const int n = d.k + d.r;
+  if (2 * n > 256) return MEC_ERR_UNSUPPORTED;
+  MEC_CUDA_OK(cudaSetDevice(device_));
+
+  FusedParams p;
+  memset(&p, 0, sizeof(p));
+  TmaMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  p.k = d.k;
+  p.r = d.r;
+  p.nblocks = d.nblocks;
+  p.S = d.S;
+  p.out = d.out;
+  p.out_pitch = d.out_pitch;
+  p.digests = d.digests;
+  p.corrupt = d.corrupt;
+  p.expect_block_stride = d.expect_block_stride;
+  for (int t = 0; t < d.k; t++) p.expect_ptr[t] = d.expect_ptr[t];
+  if (d.key) memcpy(p.key, d.key, 32);
+  if (d.r > 0 && (d.out == nullptr || (d.out_pitch & 15) || (reinterpret_cast<uintptr_t>(d.out) & 15) ||
+                  d.out_pitch < d.S))
+    return MEC_ERR_INVALID_ARGUMENT;
+
+  // ---- erasure blocks per CTA and block size
+  int eb = opt.eb > 0 ? opt.eb : (128 / (2 * n) > 0 ? 128 / (2 * n) : 1);
+  if (eb > d.nblocks) eb = static_cast<int>(d.nblocks);
+  while (eb > 1 && 2 * n * eb > 256) eb--;
+  if (eb > 255) eb = 255;
+  int threads = (2 * n * eb + 31) / 32 * 32;
+  p.eb = eb;
+
+  // ---- static / dynamic GF
+  const StaticEntry* se = nullptr;
+  if (d.static_encode && !opt.force_dynamic)
+    for (const auto& ent : kStaticTable)
+      if (ent.k == d.k && ent.m == d.r) se = &ent;
+  if (!se) {
+    if (d.r > 0 && d.coef == nullptr) return MEC_ERR_INVALID_ARGUMENT;
+    for (int j = 0; j < d.r; j++)
+      for (int t = 0; t < d.k; t++) p.coef[j][t] = d.coef[static_cast<size_t>(j) * d.k + t];
+  }
+
+  // ---- input addressing + loader choice
+  const int64_t ntiles = (static_cast<int64_t>(d.S) + kTile - 1) / kTile;
+  bool use_tma = !opt.force_bytewise && d.S > 0;
+  p.in_block_stride = d.in_block_stride;
+  if (d.contiguous) {
+    p.in_limit = d.in_block_len;
+    p.in_shard_step = d.S;
+    for (int t = 0; t < d.k; t++) {
+      p.in_ptr[t] = d.in_base + static_cast<int64_t>(t) * d.S;
+      p.in_c0[t] = static_cast<int32_t>(static_cast<int64_t>(t) * d.S);
+    }
+    const int64_t max_c0 = static_cast<int64_t>(d.k) * d.S + ntiles * kTile;
+    if ((reinterpret_cast<uintptr_t>(d.in_base) & 15) || (d.in_block_stride & 15) || max_c0 >= (1ll << 31) ||
+        d.nblocks >= (1ll << 31) || (d.nblocks > 1 && d.in_block_stride < d.in_block_len))
+      use_tma = false;
+    if (use_tma) {
+      p.tma_mode = kLoadTmaBlocks2D;
+      const uint64_t stride = d.nblocks > 1 ? static_cast<uint64_t>(d.in_block_stride)
+                                            : static_cast<uint64_t>((d.in_block_len + 15) / 16 * 16);
+      int rc = make_map(encode_tiled_, &maps.m[0], d.in_base, static_cast<uint64_t>(d.in_block_len),
+                        static_cast<uint64_t>(d.nblocks), stride, kTile, static_cast<uint32_t>(eb));
+      if (rc) return rc;
+    }
+  } else {
+    p.in_limit = d.S;
+    p.in_shard_step = 0;
+    if (d.k > kMaxMaps) use_tma = false;
+    for (int t = 0; t < d.k; t++) {
+      p.in_ptr[t] = d.in_ptr[t];
+      if (use_tma) {
+        const int64_t off = d.in_ptr[t] - d.map_base[t];
+        const int64_t max_c0 = off + (d.nblocks - 1) * d.in_block_stride + ntiles * kTile;
+        if ((reinterpret_cast<uintptr_t>(d.map_base[t]) & 15) || off < 0 || max_c0 >= (1ll << 31) ||
+            d.map_len[t] >= (1ll << 32) || d.in_block_stride >= (1ll << 31))
+          use_tma = false;
+        else
+          p.in_c0[t] = static_cast<int32_t>(off);
+      }
+    }
+    if (use_tma) {
+      p.tma_mode = kLoadTmaPerInput;
+      p.in_c0_block_step = static_cast<int32_t>(d.in_block_stride);
+      for (int t = 0; t < d.k; t++) {
+        int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], static_cast<uint64_t>(d.map_len[t]), 1,
+                          static_cast<uint64_t>((d.map_len[t] + 15) / 16 * 16), kTile, 1);
+        if (rc) return rc;
+      }
+    }
+  }
+  if (!use_tma) p.tma_mode = kLoadBytewise;
+
+  KernelFn fn;
+  if (se)
+    fn = use_tma ? se->tma : se->bytewise;
+  else
+    fn = use_tma ? static_cast<KernelFn>(fused_rs_hh_kernel<GfDynamic, true>)
+                 : static_cast<KernelFn>(fused_rs_hh_kernel<GfDynamic, false>);
+
+  const size_t smem = fused_smem_bytes(d.k, d.r, eb, se == nullptr);
+  if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;
+  MEC_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   static_cast<int>(smem)));
+  int per_sm = 0;
+  MEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  if (opt.grid_mult > 0 && opt.grid_mult < per_sm) per_sm = opt.grid_mult;
+  const int64_t ngroups = (d.nblocks + eb - 1) / eb;
+  int64_t grid = static_cast<int64_t>(per_sm) * num_sms_;
+  if (grid > ngroups) grid = ngroups;
+
+  fn<<<static_cast<unsigned>(grid), threads, smem, st>>>(p, maps);
+  MEC_CUDA_OK(cudaGetLastError());
+  launches_++;
+  return MEC_OK;
+}
+
+}  // namespace mec

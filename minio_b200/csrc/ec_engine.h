@@ -1,0 +1,82 @@
+// ec_engine.h — host-side engine behind the C ABI: kernel dispatch, tensor maps, device staging.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "ec_kernel.cuh"
+
+namespace mec {
+
+void set_last_error(const std::string& s);
+const char* get_last_error();
+
+#define MEC_CUDA_OK(expr)                                                                    \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ::mec::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));             \
+      return MEC_ERR_CUDA;                                                                   \
+    }                                                                                        \
+  } while (0)
+
+// One fused launch over `nblocks` equally shaped erasure blocks (all pointers are device pointers).
+struct FusedDesc {
+  int k = 0, r = 0;
+  const uint8_t* coef = nullptr;   // r x k row-major runtime matrix (ignored when static_encode)
+  bool static_encode = false;      // matrix == parity rows of (k, r): compile-time kernels eligible
+  int64_t nblocks = 0;
+  int32_t S = 0;
+  // input addressing
+  bool contiguous = true;          // true: Split layout inside contiguous object bytes
+  const uint8_t* in_base = nullptr;  // contiguous: first byte of block 0
+  int64_t in_block_stride = 0;     // bytes between consecutive blocks (both kinds)
+  int64_t in_block_len = 0;        // contiguous: valid object bytes per block (<= k*S)
+  const uint8_t* in_ptr[kMaxK] = {};   // !contiguous: shard t, block 0, byte 0
+  const uint8_t* map_base[kMaxK] = {}; // !contiguous: 16B-aligned base of the allocation holding input t
+  int64_t map_len[kMaxK] = {};         // !contiguous: addressable bytes from map_base[t]
+  // outputs
+  uint8_t* out = nullptr;
+  int64_t out_pitch = 0;
+  uint8_t* digests = nullptr;      // nullptr: skip hashing entirely
+  const uint8_t* expect_ptr[kMaxK] = {};
+  int64_t expect_block_stride = 0;
+  uint8_t* corrupt = nullptr;
+  const uint8_t* key = nullptr;    // 32-byte HighwayHash key (host)
+};
+
+struct EngineOptions {
+  int eb = 0;              // erasure blocks per CTA (0 = auto)
+  int force_bytewise = 0;  // 1: never use TMA
+  int force_dynamic = 0;   // 1: never use the compile-time specialised GF kernels
+  int grid_mult = 0;       // CTAs per SM (0 = occupancy)
+  int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
+};
+
+class Engine {
+ public:
+  explicit Engine(int device);
+  ~Engine();
+  int init();
+  int device() const { return device_; }
+  int launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStream_t st);
+  int64_t launches() const { return launches_; }
+  int num_sms() const { return num_sms_; }
+
+ private:
+  int device_;
+  int num_sms_ = 0;
+  void* encode_tiled_ = nullptr;  // cuTensorMapEncodeTiled
+  int64_t launches_ = 0;
+};
+
+// grow-only device / pinned buffers
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n);
+  void release();
+};
+
+}  // namespace mec

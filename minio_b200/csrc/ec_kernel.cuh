@@ -1,0 +1,348 @@
+// ec_kernel.cuh — the fused Reed-Solomon + HighwayHash-256 kernel (sm_100a).
+//
+// One launch consumes `nblocks` erasure blocks.  For each block it reads k input shards ONCE
+// (cmd/erasure-coding.go:81 Split layout for encode; surviving shards for reconstruct/heal),
+// produces r output shards (parity rows of cmd/erasure-coding.go:85, or the decode rows behind
+// :106/:112) and the HighwayHash-256 bitrot digest of every input and output shard
+// (cmd/bitrot-streaming.go:57-59 for writers, :194-196 for readers) — the two passes the
+// reference makes over each shard are one pass over shared-memory tiles here.
+//
+// Work decomposition (all integer/byte work, HBM- and ALU-issue-bound; no tensor cores):
+//   CTA     = `eb` erasure blocks, blockDim = 2*(k+r)*eb rounded up to a warp multiple
+//   tile    = 256 bytes of every shard; a 3-deep ring of input tiles is filled by TMA
+//             (cp.async.bulk.tensor, byte-granular coordinates => shards need no alignment, the
+//             zero padding of Split comes from TMA out-of-bounds fill) or by a byte-wise fallback
+//   GF step = each thread owns an 8-byte column of a tile: k LDS.64 -> r outputs -> STS.64 + STG.64
+//   HH step = two threads per shard stream (lanes {0,1} / {2,3}); streams are time-skewed by
+//             (stream & 3) packets so the four streams of a quarter-warp hit disjoint banks
+#pragma once
+#include "ec_device.cuh"
+
+namespace mec {
+
+constexpr int kTile = 256;     // bytes of one shard per tile
+constexpr int kStages = 3;     // input tile ring depth
+constexpr int kMaxK = 32;      // inputs supported by the GPU path
+constexpr int kMaxR = 16;      // outputs supported by the GPU path
+constexpr int kMaxMaps = 16;   // tensor maps carried in kernel params
+constexpr int kRChunk = 4;     // rows per pass in the runtime-matrix GF step
+
+enum LoaderMode : int { kLoadBytewise = 0, kLoadTmaBlocks2D = 1, kLoadTmaPerInput = 2 };
+
+struct alignas(64) TmaMaps {
+  CUtensorMap m[kMaxMaps];
+};
+
+struct FusedParams {
+  int k, r, eb, tma_mode;
+  int64_t nblocks;
+  int32_t S;                       // shard bytes per erasure block
+  int32_t in_c0_block_step;        // kLoadTmaPerInput: bytes between blocks in an input stream
+  int32_t in_c0[kMaxK];            // TMA byte coordinate of input t (block 0, x = 0)
+  const uint8_t* in_ptr[kMaxK];    // byte-wise loader: input t, block 0, x = 0
+  int64_t in_block_stride;         // byte-wise loader: bytes between blocks
+  int64_t in_limit, in_shard_step; // valid bytes of input t = clamp(in_limit - t*in_shard_step, 0, S)
+  uint8_t* out;                    // output shard (b, j) at out + (b*r + j) * out_pitch
+  int64_t out_pitch;               // multiple of 16
+  uint8_t* digests;                // [nblocks][k + r][32]
+  const uint8_t* expect_ptr[kMaxK];// optional expected digest of input t, block 0 (bitrot reader)
+  int64_t expect_block_stride;
+  uint8_t* corrupt;                // optional [nblocks][k], set to 1 on digest mismatch
+  uint64_t key[4];                 // HighwayHash key (cmd/bitrot.go:37 for bitrot)
+  uint8_t coef[kMaxR][kMaxK];      // runtime matrix (GfDynamic only)
+};
+
+// ------------------------------------------------------------------ GF policies
+template <int K_, int M_>
+struct GfStatic {
+  static constexpr bool kIsStatic = true;
+  static constexpr int K = K_, R = M_;
+  using Mat = EncodeMatrix<K_, M_>;
+};
+struct GfDynamic {
+  static constexpr bool kIsStatic = false;
+  static constexpr int K = 0, R = 0;
+};
+
+__host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, bool dynamic_gf) {
+  uint32_t b = 128 + 128;  // alignment slack + barriers
+  b += static_cast<uint32_t>(kStages) * k * eb * kTile;
+  b += 2u * (r > 0 ? r : 0) * eb * kTile;
+  if (dynamic_gf) b += static_cast<uint32_t>(k) * ((r + kRChunk - 1) / kRChunk) * kRChunk * 8 * 4;
+  return b;
+}
+
+#ifndef MEC_MIN_BLOCKS
+#define MEC_MIN_BLOCKS 3
+#endif
+template <class GF, bool USE_TMA>
+__global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
+                                                         const __grid_constant__ TmaMaps maps) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  const int k = GF::kIsStatic ? GF::K : p.k;
+  const int r = GF::kIsStatic ? GF::R : p.r;
+  const int eb = p.eb;
+  const int nstreams = k + r;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const bool warp0 = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;  // provably warp-uniform
+  const uint32_t stage_bytes = static_cast<uint32_t>(k) * eb * kTile;
+  const uint32_t par_bytes = static_cast<uint32_t>(r) * eb * kTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint8_t* s_data = smem + 128;
+  uint8_t* s_par = s_data + kStages * stage_bytes;
+  uint32_t* s_masks = reinterpret_cast<uint32_t*>(s_par + 2 * par_bytes);
+  const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
+
+  const int32_t S = p.S;
+  const int ntiles = (S + kTile - 1) / kTile;
+  const int npk = S >> 5, rem = S & 31;
+
+  if constexpr (USE_TMA) {
+    if (tid == 0) {
+      for (int s = 0; s < kStages; s++) mbar_init(smem_u32(&bars[s]), 1);
+      fence_barrier_init();
+    }
+  }
+  if constexpr (!GF::kIsStatic) {
+    // expand coefficient bytes into AND-masks: s_masks[(t*rpad + j)*8 + bit]
+    for (int i = tid; i < k * rpad * 8; i += nthr) {
+      const int bit = i & 7, j = (i >> 3) % rpad, t = (i >> 3) / rpad;
+      const uint32_t c = j < r ? p.coef[j][t] : 0u;
+      s_masks[i] = 0u - ((c >> bit) & 1u);
+    }
+  }
+  __syncthreads();
+
+  // ---- HighwayHash thread identity: 2 threads per stream
+  const bool hh_thread = p.digests != nullptr && tid < 2 * nstreams * eb;
+  const int sl = tid >> 1, h = tid & 1;
+  const int e_hh = hh_thread ? sl / nstreams : 0;
+  const int srow = hh_thread ? sl % nstreams : 0;
+  const int rho = sl & 3;
+  const bool is_out = srow >= k;
+  const uint32_t hh_rowoff = (is_out ? static_cast<uint32_t>((srow - k) * eb + e_hh)
+                                     : static_cast<uint32_t>(srow * eb + e_hh)) * kTile + 16u * h;
+
+  const int64_t ngroups = (p.nblocks + eb - 1) / eb;
+  uint32_t it = 0;  // running tile counter (stage / mbarrier phase bookkeeping)
+
+  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int64_t b0 = g * eb;
+    const int nb = (p.nblocks - b0) < eb ? static_cast<int>(p.nblocks - b0) : eb;
+    const bool hh_live = hh_thread && e_hh < nb;
+
+    HHHalf hs;
+    hh_init(hs, p.key, h);
+
+    // ---------------- tile loaders
+    auto issue_tile = [&](int i, uint32_t stage) {  // USE_TMA: called by thread 0 only
+      if constexpr (USE_TMA) {
+        const uint32_t bar = smem_u32(&bars[stage]);
+        const uint32_t dst0 = smem_u32(s_data + stage * stage_bytes);
+        if (p.tma_mode == kLoadTmaBlocks2D) {
+          mbar_expect_tx(bar, stage_bytes);
+          for (int t = 0; t < k; t++)
+            tma_load_2d(dst0 + static_cast<uint32_t>(t * eb) * kTile, &maps.m[0], p.in_c0[t] + i * kTile,
+                        static_cast<int32_t>(b0), bar);
+        } else {
+          mbar_expect_tx(bar, static_cast<uint32_t>(k) * nb * kTile);
+          for (int t = 0; t < k; t++)
+            for (int e = 0; e < nb; e++)
+              tma_load_2d(dst0 + static_cast<uint32_t>(t * eb + e) * kTile, &maps.m[t],
+                          p.in_c0[t] + static_cast<int32_t>(b0 + e) * p.in_c0_block_step + i * kTile, 0, bar);
+        }
+      } else {
+        uint8_t* dst = s_data + stage * stage_bytes;
+        const int per_t = eb * kTile;
+        for (int idx = tid; idx < k * per_t; idx += nthr) {
+          const int t = idx / per_t, q = idx - t * per_t, e = q >> 8, x = q & (kTile - 1);
+          const int64_t xg = static_cast<int64_t>(i) * kTile + x;
+          int64_t valid = p.in_limit - static_cast<int64_t>(t) * p.in_shard_step;
+          valid = valid < 0 ? 0 : (valid > S ? S : valid);
+          uint8_t v = 0;
+          if (e < nb && xg < valid) v = p.in_ptr[t][(b0 + e) * p.in_block_stride + xg];
+          dst[idx] = v;
+        }
+      }
+    };
+
+    if constexpr (USE_TMA) {
+      if (warp0) {
+        if (elect_one()) {
+          if (ntiles > 0) issue_tile(0, it % kStages);
+          if (ntiles > 1) issue_tile(1, (it + 1) % kStages);
+        }
+        __syncwarp();
+      }
+    } else {
+      if (ntiles > 0) issue_tile(0, it % kStages);
+      if (ntiles > 1) issue_tile(1, (it + 1) % kStages);
+      __syncthreads();
+    }
+
+    // ---------------- HH window: packets [8i - rho, 8i + 8 - rho) clipped to [0, npk)
+    auto hh_window = [&](int i, uint32_t st_prev, uint32_t st_cur) {
+      if (!hh_live) return;
+      const uint8_t* base_prev = is_out ? s_par + ((i - 1) & 1) * par_bytes : s_data + st_prev * stage_bytes;
+      const uint8_t* base_cur = is_out ? s_par + (i & 1) * par_bytes : s_data + st_cur * stage_bytes;
+      const uint32_t a_prev = smem_u32(base_prev) + hh_rowoff + (8 - rho) * 32;
+      const uint32_t a_cur = smem_u32(base_cur) + hh_rowoff - rho * 32;
+      const int q0 = 8 * i - rho;
+      if (q0 >= 0 && q0 + 8 <= npk) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const uint32_t a = (j < 3 && rho > j) ? a_prev : a_cur;
+          const uint4 v = lds128(a + 32 * j);
+          hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
+        }
+      } else {
+#pragma unroll 1
+        for (int j = 0; j < 8; j++) {
+          const int q = q0 + j;
+          if (q < 0 || q >= npk) continue;
+          const uint32_t a = (rho > j) ? a_prev : a_cur;
+          const uint4 v = lds128(a + 32 * j);
+          hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
+        }
+      }
+    };
+
+    // ---------------- main tile loop
+    for (int i = 0; i < ntiles; i++) {
+      const uint32_t st_cur = (it + i) % kStages;
+      const uint32_t st_prev = (it + i + kStages - 1) % kStages;
+      if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[st_cur]), ((it + i) / kStages) & 1u);
+
+      // ---- GF step on tile i -> output tile (i & 1) in smem + global
+      if (r > 0) {
+        const uint8_t* din = s_data + st_cur * stage_bytes;
+        uint8_t* dpar = s_par + (i & 1) * par_bytes;
+        const int ncol = eb * (kTile / 8);
+        for (int c = tid; c < ncol; c += nthr) {
+          const int e = c >> 5, x8 = c & 31;
+          const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
+          const bool store_ok = e < nb && xg < S;
+          if constexpr (GF::kIsStatic) {
+            constexpr int K = GF::K, R = GF::R;
+            uint32_t lo[K], hi[K], olo[R], ohi[R];
+#pragma unroll
+            for (int t = 0; t < K; t++) {
+              const uint2 v = *reinterpret_cast<const uint2*>(din + (t * eb + e) * kTile + x8 * 8);
+              lo[t] = v.x; hi[t] = v.y;
+            }
+            GfStaticApply<typename GF::Mat>::run(lo, olo);
+            GfStaticApply<typename GF::Mat>::run(hi, ohi);
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+              const uint2 o = make_uint2(olo[j], ohi[j]);
+              *reinterpret_cast<uint2*>(dpar + (j * eb + e) * kTile + x8 * 8) = o;
+              if (store_ok) {
+                uint8_t* gp = p.out + ((b0 + e) * R + j) * p.out_pitch + xg;
+                if (xg + 8 <= S) {
+                  *reinterpret_cast<uint2*>(gp) = o;
+                } else {
+                  const uint64_t w = pack64(o.x, o.y);
+                  for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
+                }
+              }
+            }
+          } else {
+            for (int j0 = 0; j0 < r; j0 += kRChunk) {
+              uint32_t pl[kRChunk][8], ph[kRChunk][8];
+#pragma unroll
+              for (int j = 0; j < kRChunk; j++)
+#pragma unroll
+                for (int b = 0; b < 8; b++) { pl[j][b] = 0u; ph[j][b] = 0u; }
+#pragma unroll 2
+              for (int t = 0; t < k; t++) {
+                const uint2 v = *reinterpret_cast<const uint2*>(din + (t * eb + e) * kTile + x8 * 8);
+                const uint4* mk = reinterpret_cast<const uint4*>(s_masks + (t * rpad + j0) * 8);
+#pragma unroll
+                for (int j = 0; j < kRChunk; j++) {
+                  const uint4 m0 = mk[2 * j], m1 = mk[2 * j + 1];
+                  pl[j][0] ^= v.x & m0.x; ph[j][0] ^= v.y & m0.x;
+                  pl[j][1] ^= v.x & m0.y; ph[j][1] ^= v.y & m0.y;
+                  pl[j][2] ^= v.x & m0.z; ph[j][2] ^= v.y & m0.z;
+                  pl[j][3] ^= v.x & m0.w; ph[j][3] ^= v.y & m0.w;
+                  pl[j][4] ^= v.x & m1.x; ph[j][4] ^= v.y & m1.x;
+                  pl[j][5] ^= v.x & m1.y; ph[j][5] ^= v.y & m1.y;
+                  pl[j][6] ^= v.x & m1.z; ph[j][6] ^= v.y & m1.z;
+                  pl[j][7] ^= v.x & m1.w; ph[j][7] ^= v.y & m1.w;
+                }
+              }
+#pragma unroll
+              for (int j = 0; j < kRChunk; j++) {
+                if (j0 + j >= r) break;
+                uint32_t al = pl[j][7], ah = ph[j][7];
+#pragma unroll
+                for (int b = 6; b >= 0; b--) {
+                  al = gf_xtime4(al) ^ pl[j][b];
+                  ah = gf_xtime4(ah) ^ ph[j][b];
+                }
+                const uint2 o = make_uint2(al, ah);
+                *reinterpret_cast<uint2*>(dpar + ((j0 + j) * eb + e) * kTile + x8 * 8) = o;
+                if (store_ok) {
+                  uint8_t* gp = p.out + ((b0 + e) * r + (j0 + j)) * p.out_pitch + xg;
+                  if (xg + 8 <= S) {
+                    *reinterpret_cast<uint2*>(gp) = o;
+                  } else {
+                    const uint64_t w = pack64(o.x, o.y);
+                    for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();  // (A) output tile i visible to the hash threads
+
+      hh_window(i, st_prev, st_cur);
+
+      __syncthreads();  // (B) tile i-1 (input stage + output buffer) is now free
+      if (i + 2 < ntiles) {
+        if constexpr (USE_TMA) {
+          if (warp0) {
+            if (elect_one()) issue_tile(i + 2, (it + i + 2) % kStages);
+            __syncwarp();
+          }
+        } else {
+          issue_tile(i + 2, (it + i + 2) % kStages);
+        }
+      }
+    }
+
+    // ---------------- drain the skewed packets, remainder bytes, finalisation
+    {
+      const uint32_t st_last = (it + (ntiles > 0 ? ntiles - 1 : 0)) % kStages;
+      if (ntiles > 0) hh_window(ntiles, st_last, st_last);
+      if (hh_live && rem) {
+        const uint8_t* base = is_out ? s_par + ((ntiles - 1) & 1) * par_bytes : s_data + st_last * stage_bytes;
+        const uint8_t* tail = base + (hh_rowoff - 16u * h) + ((npk * 32) & (kTile - 1));
+        hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
+      }
+      uint64_t d0, d1;
+      hh_finalize(hs, d0, d1);  // all threads of the warp take part in the shuffles
+      if (hh_live) {
+        const int64_t b = b0 + e_hh;
+        uint64_t* dg = reinterpret_cast<uint64_t*>(p.digests + (b * nstreams + srow) * 32 + 16 * h);
+        dg[0] = d0;
+        dg[1] = d1;
+        if (!is_out && p.corrupt != nullptr && p.expect_ptr[srow] != nullptr) {
+          const uint8_t* ex = p.expect_ptr[srow] + b * p.expect_block_stride + 16 * h;
+          uint64_t e0 = 0, e1 = 0;
+          for (int q = 0; q < 8; q++) {
+            e0 |= static_cast<uint64_t>(ex[q]) << (8 * q);
+            e1 |= static_cast<uint64_t>(ex[8 + q]) << (8 * q);
+          }
+          if (e0 != d0 || e1 != d1) p.corrupt[b * k + srow] = 1;
+        }
+      }
+    }
+    __syncthreads();  // stages are reused by the next group's prologue
+    it += static_cast<uint32_t>(ntiles);
+  }
+}
+
+}  // namespace mec
