@@ -279,7 +279,22 @@ extern "C" int64_t mec_encode(mec_codec* c, const uint8_t* src, int64_t len, uin
 struct FrameGeom {
   int64_t nblocks, S, last_len;
   int64_t file_bytes() const { return nblocks <= 0 ? 0 : (nblocks - 1) * (32 + S) + 32 + last_len; }
+  // frames are staged on the device at a 16-byte aligned pitch so that every TMA row is aligned
+  int64_t dpitch() const { return round_up(32 + S, 16); }
+  int64_t dev_bytes() const { return nblocks * dpitch() + 512; }
 };
+
+// host frames ([32+S] stride, last frame possibly short) -> device frames at pitch g.dpitch()
+static int stage_frames(const uint8_t* host, void* dev, const FrameGeom& g, cudaStream_t st) {
+  const int64_t nfull = (g.last_len == g.S) ? g.nblocks : g.nblocks - 1;
+  if (nfull > 0)
+    MEC_CUDA_OK(cudaMemcpy2DAsync(dev, static_cast<size_t>(g.dpitch()), host, static_cast<size_t>(32 + g.S),
+                                  static_cast<size_t>(32 + g.S), static_cast<size_t>(nfull), cudaMemcpyHostToDevice, st));
+  if (nfull < g.nblocks)
+    MEC_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(dev) + nfull * g.dpitch(), host + nfull * (32 + g.S),
+                                static_cast<size_t>(32 + g.last_len), cudaMemcpyHostToDevice, st));
+  return MEC_OK;
+}
 
 // Rebuild shards `targets` for blocks [0, g.nblocks) from the staged survivor files chosen[0..k).
 // d_out rows: (b*r + q); digests [b][k + r]; flags [b][k].
@@ -288,7 +303,7 @@ static int launch_reconstruct(mec_codec* c, const FrameGeom& g, int64_t cur, con
                               cudaStream_t st) {
   FusedDesc d;
   d.k = c->k; d.r = r; d.coef = rows; d.static_encode = false; d.contiguous = false;
-  d.key = kMagicKey; d.out_pitch = pitch; d.expect_block_stride = 32 + g.S; d.in_block_stride = 32 + g.S;
+  d.key = kMagicKey; d.out_pitch = pitch; d.expect_block_stride = g.dpitch(); d.in_block_stride = g.dpitch();
   // blocks [cur, g.nblocks) of the staged files; outputs are indexed from block `cur`
   const int64_t nfull_all = (g.last_len == g.S) ? g.nblocks : g.nblocks - 1;
   for (int pass = 0; pass < 2; pass++) {
@@ -300,9 +315,9 @@ static int launch_reconstruct(mec_codec* c, const FrameGeom& g, int64_t cur, con
     for (int t = 0; t < c->k; t++) {
       const uint8_t* base = static_cast<const uint8_t*>(c->in_files[chosen[t]].p);
       d.map_base[t] = base;
-      d.map_len[t] = g.file_bytes();
-      d.expect_ptr[t] = base + first * (32 + g.S);
-      d.in_ptr[t] = base + first * (32 + g.S) + 32;
+      d.map_len[t] = g.dev_bytes();
+      d.expect_ptr[t] = base + first * g.dpitch();
+      d.in_ptr[t] = base + first * g.dpitch() + 32;
     }
     d.out = d_out + (first - cur) * r * pitch;
     d.digests = d_dig + (first - cur) * (c->k + r) * 32;
@@ -342,8 +357,8 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
     for (int t = 0; t < k; t++) {
       const int i = chosen[t];
       if (staged[i]) continue;
-      if ((rc = c->in_files[i].ensure(static_cast<size_t>(g.file_bytes() + 512)))) return rc;
-      MEC_CUDA_OK(cudaMemcpyAsync(c->in_files[i].p, frames[i], static_cast<size_t>(g.file_bytes()), cudaMemcpyHostToDevice, st));
+      if ((rc = c->in_files[i].ensure(static_cast<size_t>(g.dev_bytes())))) return rc;
+      if ((rc = stage_frames(frames[i], c->in_files[i].p, g, st))) return rc;
       staged[i] = 1;
     }
     FrameGeom sub = g;
@@ -509,23 +524,25 @@ extern "C" int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file
   MEC_CUDA_OK(cudaSetDevice(c->device));
   Slot& s = c->slots[0];
   const int64_t nblocks = ceil_frac(part_len, S), last_len = part_len - (nblocks - 1) * S;
-  if ((rc = s.src.ensure(static_cast<size_t>(file_len + 512)))) return rc;
+  FrameGeom g{nblocks, S, last_len};
+  const int64_t P = g.dpitch();
+  if ((rc = s.src.ensure(static_cast<size_t>(g.dev_bytes())))) return rc;
   if ((rc = s.dig.ensure(static_cast<size_t>(nblocks * 32)))) return rc;
   if ((rc = c->flags.ensure(static_cast<size_t>(nblocks)))) return rc;
-  MEC_CUDA_OK(cudaMemcpyAsync(s.src.p, file, static_cast<size_t>(file_len), cudaMemcpyHostToDevice, s.st));
+  if ((rc = stage_frames(file, s.src.p, g, s.st))) return rc;
   MEC_CUDA_OK(cudaMemsetAsync(c->flags.p, 0, static_cast<size_t>(nblocks), s.st));
   FusedDesc d;
   d.k = 1; d.r = 0; d.contiguous = false; d.key = kMagicKey;
-  d.in_block_stride = 32 + S; d.expect_block_stride = 32 + S;
+  d.in_block_stride = P; d.expect_block_stride = P;
   const uint8_t* base = static_cast<const uint8_t*>(s.src.p);
   const int64_t nfull = last_len == S ? nblocks : nblocks - 1;
   for (int pass = 0; pass < 2; pass++) {
     const int64_t first = pass == 0 ? 0 : nfull, nb = pass == 0 ? nfull : nblocks - nfull;
     if (nb <= 0) continue;
     d.nblocks = nb; d.S = static_cast<int32_t>(pass == 0 ? S : last_len);
-    d.map_base[0] = base; d.map_len[0] = file_len;
-    d.expect_ptr[0] = base + first * (32 + S);
-    d.in_ptr[0] = base + first * (32 + S) + 32;
+    d.map_base[0] = base; d.map_len[0] = g.dev_bytes();
+    d.expect_ptr[0] = base + first * P;
+    d.in_ptr[0] = base + first * P + 32;
     d.digests = static_cast<uint8_t*>(s.dig.p) + first * 32;
     d.corrupt = static_cast<uint8_t*>(c->flags.p) + first;
     if ((rc = c->eng->launch_fused(d, c->opt, s.st))) return rc;
@@ -616,16 +633,18 @@ extern "C" int mec_hh256_batch(mec_codec* c, const uint8_t* msgs, int64_t msg_le
   MEC_CUDA_OK(cudaSetDevice(c->device));
   Slot& s = c->slots[0];
   if ((rc = s.dig.ensure(static_cast<size_t>(count * 32)))) return rc;
-  if ((rc = s.src.ensure(static_cast<size_t>(count * msg_len + 512)))) return rc;
+  const int64_t mp = std::max<int64_t>(round_up(msg_len, 16), 16);
+  if ((rc = s.src.ensure(static_cast<size_t>(count * mp + 512)))) return rc;
   if (msg_len > 0)
-    MEC_CUDA_OK(cudaMemcpyAsync(s.src.p, msgs, static_cast<size_t>(count * msg_len), cudaMemcpyHostToDevice, s.st));
+    MEC_CUDA_OK(cudaMemcpy2DAsync(s.src.p, static_cast<size_t>(mp), msgs, static_cast<size_t>(msg_len),
+                                  static_cast<size_t>(msg_len), static_cast<size_t>(count), cudaMemcpyHostToDevice, s.st));
   FusedDesc d;
   d.k = 1; d.r = 0; d.contiguous = false; d.key = kMagicKey;
   d.nblocks = count; d.S = static_cast<int32_t>(msg_len);
-  d.in_block_stride = msg_len;
+  d.in_block_stride = mp;
   d.in_ptr[0] = static_cast<const uint8_t*>(s.src.p);
   d.map_base[0] = d.in_ptr[0];
-  d.map_len[0] = std::max<int64_t>(count * msg_len, 16);
+  d.map_len[0] = count * mp + 256;
   d.digests = static_cast<uint8_t*>(s.dig.p);
   if ((rc = c->eng->launch_fused(d, c->opt, s.st))) return rc;
   MEC_CUDA_OK(cudaMemcpyAsync(digests, s.dig.p, static_cast<size_t>(count * 32), cudaMemcpyDeviceToHost, s.st));

@@ -28,19 +28,21 @@ void DevBuf::release() {
 // (k, m) pairs with compile-time specialised GF code.  MinIO's default parity for a 16-drive set
 // is EC:4 => RS(12,4) (internal/config/storageclass/storage-class.go:355); the others are the
 // BASELINE configs and common set sizes.
-#define MEC_STATIC_CONFIGS(X) X(12, 4) X(4, 2) X(16, 4) X(8, 8) X(8, 4) X(6, 2) X(10, 4) X(14, 2) X(2, 2)
+#define MEC_STATIC_CONFIGS(X) X(12, 4) X(4, 2) X(16, 4) X(8, 8) X(8, 4) X(6, 2) X(2, 2)
 
 using KernelFn = void (*)(const FusedParams, const TmaMaps);
 
 struct StaticEntry {
   int k, m;
-  KernelFn tma, bytewise;
+  KernelFn fn[3];  // indexed by loader: 0 byte-wise, 1 TMA aligned, 2 TMA + re-align
 };
 static const StaticEntry kStaticTable[] = {
-#define X(K, M) {K, M, fused_rs_hh_kernel<GfStatic<K, M>, true>, fused_rs_hh_kernel<GfStatic<K, M>, false>},
+#define X(K, M) {K, M, {fused_rs_hh_kernel<GfStatic<K, M>, 0>, fused_rs_hh_kernel<GfStatic<K, M>, 1>, fused_rs_hh_kernel<GfStatic<K, M>, 2>}},
     MEC_STATIC_CONFIGS(X)
 #undef X
 };
+static const KernelFn kDynamicFn[3] = {fused_rs_hh_kernel<GfDynamic, 0>, fused_rs_hh_kernel<GfDynamic, 1>,
+                                       fused_rs_hh_kernel<GfDynamic, 2>};
 
 Engine::Engine(int device) : device_(device) {}
 Engine::~Engine() {}
@@ -80,7 +82,7 @@ static int make_map(void* fn, CUtensorMap* map, const void* base, uint64_t dim0,
   cuuint64_t strides[1] = {stride1};
   cuuint32_t box[2] = {box0, box1};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base),
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base),
                                                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -137,65 +139,68 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       for (int t = 0; t < d.k; t++) p.coef[j][t] = d.coef[static_cast<size_t>(j) * d.k + t];
   }
 
-  // ---- input addressing + loader choice
+  // ---- input addressing + loader choice.  TMA boxes must start on 16-byte boundaries, so each row is
+  // fetched from the aligned-down address and the kernel skips in_align[t] bytes.
   const int64_t ntiles = (static_cast<int64_t>(d.S) + kTile - 1) / kTile;
   bool use_tma = !opt.force_bytewise && d.S > 0;
+  bool any_misaligned = false;
   p.in_block_stride = d.in_block_stride;
+  p.raw_pitch = kRawRow;
   if (d.contiguous) {
     p.in_limit = d.in_block_len;
     p.in_shard_step = d.S;
-    for (int t = 0; t < d.k; t++) {
-      p.in_ptr[t] = d.in_base + static_cast<int64_t>(t) * d.S;
-      p.in_c0[t] = static_cast<int32_t>(static_cast<int64_t>(t) * d.S);
-    }
-    const int64_t max_c0 = static_cast<int64_t>(d.k) * d.S + ntiles * kTile;
-    if ((reinterpret_cast<uintptr_t>(d.in_base) & 15) || (d.in_block_stride & 15) || max_c0 >= (1ll << 31) ||
-        d.nblocks >= (1ll << 31) || (d.nblocks > 1 && d.in_block_stride < d.in_block_len))
+    const int64_t max_c0 = static_cast<int64_t>(d.k) * d.S + ntiles * kTile + 64;
+    if ((reinterpret_cast<uintptr_t>(d.in_base) & 15) || (d.in_block_stride & 15) || (d.in_block_len & 15) ||
+        max_c0 >= (1ll << 31) || d.nblocks >= (1ll << 31) || (d.nblocks > 1 && d.in_block_stride < d.in_block_len))
       use_tma = false;
+    for (int t = 0; t < d.k; t++) {
+      const int64_t off = static_cast<int64_t>(t) * d.S;
+      p.in_ptr[t] = d.in_base + off;
+      p.in_c0[t] = static_cast<int32_t>(off & ~15ll);
+      p.in_align[t] = static_cast<uint8_t>(off & 15);
+      any_misaligned |= (off & 15) != 0;
+    }
     if (use_tma) {
       p.tma_mode = kLoadTmaBlocks2D;
-      const uint64_t stride = d.nblocks > 1 ? static_cast<uint64_t>(d.in_block_stride)
-                                            : static_cast<uint64_t>((d.in_block_len + 15) / 16 * 16);
-      int rc = make_map(encode_tiled_, &maps.m[0], d.in_base, static_cast<uint64_t>(d.in_block_len),
-                        static_cast<uint64_t>(d.nblocks), stride, kTile, static_cast<uint32_t>(eb));
+      const uint64_t stride = d.nblocks > 1 ? static_cast<uint64_t>(d.in_block_stride) : static_cast<uint64_t>(d.in_block_len);
+      int rc = make_map(encode_tiled_, &maps.m[0], d.in_base, static_cast<uint64_t>(d.in_block_len / 4),
+                        static_cast<uint64_t>(d.nblocks), stride, kRawRow / 4, static_cast<uint32_t>(eb));
       if (rc) return rc;
     }
   } else {
     p.in_limit = d.S;
     p.in_shard_step = 0;
-    if (d.k > kMaxMaps) use_tma = false;
+    if (d.k > kMaxMaps || (d.in_block_stride & 15)) use_tma = false;
     for (int t = 0; t < d.k; t++) {
       p.in_ptr[t] = d.in_ptr[t];
-      if (use_tma) {
-        const int64_t off = d.in_ptr[t] - d.map_base[t];
-        const int64_t max_c0 = off + (d.nblocks - 1) * d.in_block_stride + ntiles * kTile;
-        if ((reinterpret_cast<uintptr_t>(d.map_base[t]) & 15) || off < 0 || max_c0 >= (1ll << 31) ||
-            d.map_len[t] >= (1ll << 32) || d.in_block_stride >= (1ll << 31))
-          use_tma = false;
-        else
-          p.in_c0[t] = static_cast<int32_t>(off);
+      if (!use_tma) continue;
+      const int64_t off = d.in_ptr[t] - d.map_base[t];
+      const int64_t max_c0 = off + (d.nblocks - 1) * d.in_block_stride + ntiles * kTile + 64;
+      if ((reinterpret_cast<uintptr_t>(d.map_base[t]) & 15) || off < 0 || max_c0 >= (1ll << 31) ||
+          d.map_len[t] >= (1ll << 33) || d.in_block_stride >= (1ll << 31)) {
+        use_tma = false;
+      } else {
+        p.in_c0[t] = static_cast<int32_t>(off & ~15ll);
+        p.in_align[t] = static_cast<uint8_t>(off & 15);
+        any_misaligned |= (off & 15) != 0;
       }
     }
     if (use_tma) {
       p.tma_mode = kLoadTmaPerInput;
+      p.raw_pitch = 384;  // every (input, block) row is its own TMA box: destinations must be 128B-aligned
       p.in_c0_block_step = static_cast<int32_t>(d.in_block_stride);
       for (int t = 0; t < d.k; t++) {
-        int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], static_cast<uint64_t>(d.map_len[t]), 1,
-                          static_cast<uint64_t>((d.map_len[t] + 15) / 16 * 16), kTile, 1);
+        const uint64_t elems = static_cast<uint64_t>((d.map_len[t] + 3) / 4);
+        int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], elems, 1, (elems * 4 + 15) / 16 * 16, kRawRow / 4, 1);
         if (rc) return rc;
       }
     }
   }
+  const int loader = !use_tma ? 0 : (any_misaligned ? 2 : 1);
   if (!use_tma) p.tma_mode = kLoadBytewise;
 
-  KernelFn fn;
-  if (se)
-    fn = use_tma ? se->tma : se->bytewise;
-  else
-    fn = use_tma ? static_cast<KernelFn>(fused_rs_hh_kernel<GfDynamic, true>)
-                 : static_cast<KernelFn>(fused_rs_hh_kernel<GfDynamic, false>);
-
-  const size_t smem = fused_smem_bytes(d.k, d.r, eb, se == nullptr);
+  KernelFn fn = se ? se->fn[loader] : kDynamicFn[loader];
+  const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr);
   if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;
   MEC_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    static_cast<int>(smem)));

@@ -7,25 +7,30 @@
 // (cmd/bitrot-streaming.go:57-59 for writers, :194-196 for readers) — the two passes the
 // reference makes over each shard are one pass over shared-memory tiles here.
 //
-// Work decomposition (all integer/byte work, HBM- and ALU-issue-bound; no tensor cores):
-//   CTA     = `eb` erasure blocks, blockDim = 2*(k+r)*eb rounded up to a warp multiple
-//   tile    = 256 bytes of every shard; a 3-deep ring of input tiles is filled by TMA
-//             (cp.async.bulk.tensor, byte-granular coordinates => shards need no alignment, the
-//             zero padding of Split comes from TMA out-of-bounds fill) or by a byte-wise fallback
-//   GF step = each thread owns an 8-byte column of a tile: k LDS.64 -> r outputs -> STS.64 + STG.64
-//   HH step = two threads per shard stream (lanes {0,1} / {2,3}); streams are time-skewed by
-//             (stream & 3) packets so the four streams of a quarter-warp hit disjoint banks
+// Work decomposition (all integer/byte work, HBM- and issue-bound; no tensor cores):
+//   CTA      = `eb` erasure blocks, blockDim = 2*(k+r)*eb rounded up to a warp multiple
+//   tile     = 256 bytes of every shard.  Shards start at arbitrary byte offsets of the object
+//              (S = ceil(blockSize/k) is 87382 for RS(12,4)@1MiB) but TMA boxes must start on 16-byte
+//              boundaries, so each row is fetched as the 272-byte 16B-aligned superset into a 2-deep
+//              ring (cp.async.bulk.tensor, u32 elements; Split's zero padding = TMA OOB fill)
+//   GF step  = each thread owns an 8-byte column: per row 3 LDS.32 + 2 PRMT re-align the bytes in
+//              registers (or one LDS.64 when every row is 16B-aligned), the aligned column is
+//              re-stored for the hash threads, r outputs are computed -> STS.64 + STG.64
+//   HH step  = two threads per shard stream (64-bit lanes {0,1} / {2,3}); rows of the aligned tile
+//              have a 288-byte pitch so the four streams of a quarter-warp hit disjoint banks
 #pragma once
 #include "ec_device.cuh"
 
 namespace mec {
 
-constexpr int kTile = 256;     // bytes of one shard per tile
-constexpr int kStages = 3;     // input tile ring depth
-constexpr int kMaxK = 32;      // inputs supported by the GPU path
-constexpr int kMaxR = 16;      // outputs supported by the GPU path
-constexpr int kMaxMaps = 16;   // tensor maps carried in kernel params
-constexpr int kRChunk = 4;     // rows per pass in the runtime-matrix GF step
+constexpr int kTile = 256;       // bytes of one shard per tile
+constexpr int kRawRow = 272;     // 16B-aligned superset of a tile row
+constexpr int kRowPitch = 288;   // pitch of the aligned data / output tiles (bank skew of 32 B)
+constexpr int kStages = 2;       // raw tile ring depth
+constexpr int kMaxK = 32;        // inputs supported by the GPU path
+constexpr int kMaxR = 16;        // outputs supported by the GPU path
+constexpr int kMaxMaps = 16;     // tensor maps carried in kernel params
+constexpr int kRChunk = 4;       // rows per pass in the runtime-matrix GF step
 
 enum LoaderMode : int { kLoadBytewise = 0, kLoadTmaBlocks2D = 1, kLoadTmaPerInput = 2 };
 
@@ -35,16 +40,18 @@ struct alignas(64) TmaMaps {
 
 struct FusedParams {
   int k, r, eb, tma_mode;
+  int raw_pitch;                   // bytes between erasure blocks inside a raw row group (272, or 384 when every row is its own TMA box)
   int64_t nblocks;
   int32_t S;                       // shard bytes per erasure block
-  int32_t in_c0_block_step;        // kLoadTmaPerInput: bytes between blocks in an input stream
-  int32_t in_c0[kMaxK];            // TMA byte coordinate of input t (block 0, x = 0)
+  int32_t in_c0_block_step;        // kLoadTmaPerInput: bytes between blocks in an input stream (multiple of 16)
+  int32_t in_c0[kMaxK];            // TMA: 16B-aligned byte coordinate of input t (block 0, x = 0)
+  uint8_t in_align[kMaxK];         // TMA: bytes to skip at the start of each raw row (0..15)
   const uint8_t* in_ptr[kMaxK];    // byte-wise loader: input t, block 0, x = 0
   int64_t in_block_stride;         // byte-wise loader: bytes between blocks
   int64_t in_limit, in_shard_step; // valid bytes of input t = clamp(in_limit - t*in_shard_step, 0, S)
   uint8_t* out;                    // output shard (b, j) at out + (b*r + j) * out_pitch
   int64_t out_pitch;               // multiple of 16
-  uint8_t* digests;                // [nblocks][k + r][32]
+  uint8_t* digests;                // [nblocks][k + r][32]; nullptr = no hashing
   const uint8_t* expect_ptr[kMaxK];// optional expected digest of input t, block 0 (bitrot reader)
   int64_t expect_block_stride;
   uint8_t* corrupt;                // optional [nblocks][k], set to 1 on digest mismatch
@@ -64,10 +71,12 @@ struct GfDynamic {
   static constexpr int K = 0, R = 0;
 };
 
-__host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, bool dynamic_gf) {
+__host__ __device__ inline uint32_t raw_group_bytes(int eb, int raw_pitch) { return (static_cast<uint32_t>(eb) * raw_pitch + 127u) & ~127u; }
+
+__host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, int raw_pitch, bool dynamic_gf) {
   uint32_t b = 128 + 128;  // alignment slack + barriers
-  b += static_cast<uint32_t>(kStages) * k * eb * kTile;
-  b += 2u * (r > 0 ? r : 0) * eb * kTile;
+  b += static_cast<uint32_t>(kStages) * k * raw_group_bytes(eb, raw_pitch);
+  b += static_cast<uint32_t>(k + (r > 0 ? r : 0)) * eb * kRowPitch;
   if (dynamic_gf) b += static_cast<uint32_t>(k) * ((r + kRChunk - 1) / kRChunk) * kRChunk * 8 * 4;
   return b;
 }
@@ -75,9 +84,13 @@ __host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, bool 
 #ifndef MEC_MIN_BLOCKS
 #define MEC_MIN_BLOCKS 3
 #endif
-template <class GF, bool USE_TMA>
+
+// LOADER: 0 = byte-wise fallback, 1 = TMA with every row 16B-aligned, 2 = TMA + register re-alignment
+template <class GF, int LOADER>
 __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
-                                                         const __grid_constant__ TmaMaps maps) {
+                                                                         const __grid_constant__ TmaMaps maps) {
+  constexpr bool USE_TMA = LOADER != 0;
+  constexpr bool REALIGN = LOADER == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int k = GF::kIsStatic ? GF::K : p.k;
@@ -86,12 +99,14 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
   const int nstreams = k + r;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const bool warp0 = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;  // provably warp-uniform
-  const uint32_t stage_bytes = static_cast<uint32_t>(k) * eb * kTile;
-  const uint32_t par_bytes = static_cast<uint32_t>(r) * eb * kTile;
+  const uint32_t rawp = static_cast<uint32_t>(p.raw_pitch);
+  const uint32_t group_bytes = raw_group_bytes(eb, p.raw_pitch);
+  const uint32_t stage_bytes = static_cast<uint32_t>(k) * group_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint8_t* s_data = smem + 128;
-  uint8_t* s_par = s_data + kStages * stage_bytes;
-  uint32_t* s_masks = reinterpret_cast<uint32_t*>(s_par + 2 * par_bytes);
+  uint8_t* s_raw = smem + 128;
+  uint8_t* s_clean = s_raw + kStages * stage_bytes;                          // [eb][k][kRowPitch]
+  uint8_t* s_par = s_clean + static_cast<uint32_t>(k) * eb * kRowPitch;      // [eb][r][kRowPitch]
+  uint32_t* s_masks = reinterpret_cast<uint32_t*>(s_par + static_cast<uint32_t>(r) * eb * kRowPitch);
   const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
 
   const int32_t S = p.S;
@@ -119,10 +134,10 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
   const int sl = tid >> 1, h = tid & 1;
   const int e_hh = hh_thread ? sl / nstreams : 0;
   const int srow = hh_thread ? sl % nstreams : 0;
-  const int rho = sl & 3;
   const bool is_out = srow >= k;
-  const uint32_t hh_rowoff = (is_out ? static_cast<uint32_t>((srow - k) * eb + e_hh)
-                                     : static_cast<uint32_t>(srow * eb + e_hh)) * kTile + 16u * h;
+  const uint8_t* hh_row = is_out ? s_par + static_cast<uint32_t>(e_hh * r + (srow - k)) * kRowPitch
+                                 : s_clean + static_cast<uint32_t>(e_hh * k + srow) * kRowPitch;
+  const uint32_t hh_addr = smem_u32(hh_row) + 16u * h;
 
   const int64_t ngroups = (p.nblocks + eb - 1) / eb;
   uint32_t it = 0;  // running tile counter (stage / mbarrier phase bookkeeping)
@@ -136,24 +151,24 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
     hh_init(hs, p.key, h);
 
     // ---------------- tile loaders
-    auto issue_tile = [&](int i, uint32_t stage) {  // USE_TMA: called by thread 0 only
+    auto issue_tile = [&](int i, uint32_t stage) {  // TMA: one elected lane; byte-wise: all threads
       if constexpr (USE_TMA) {
         const uint32_t bar = smem_u32(&bars[stage]);
-        const uint32_t dst0 = smem_u32(s_data + stage * stage_bytes);
+        const uint32_t dst0 = smem_u32(s_raw + stage * stage_bytes);
         if (p.tma_mode == kLoadTmaBlocks2D) {
-          mbar_expect_tx(bar, stage_bytes);
+          mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
           for (int t = 0; t < k; t++)
-            tma_load_2d(dst0 + static_cast<uint32_t>(t * eb) * kTile, &maps.m[0], p.in_c0[t] + i * kTile,
+            tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
                         static_cast<int32_t>(b0), bar);
         } else {
-          mbar_expect_tx(bar, static_cast<uint32_t>(k) * nb * kTile);
+          mbar_expect_tx(bar, static_cast<uint32_t>(k) * nb * kRawRow);
           for (int t = 0; t < k; t++)
             for (int e = 0; e < nb; e++)
-              tma_load_2d(dst0 + static_cast<uint32_t>(t * eb + e) * kTile, &maps.m[t],
-                          p.in_c0[t] + static_cast<int32_t>(b0 + e) * p.in_c0_block_step + i * kTile, 0, bar);
+              tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes + e * rawp, &maps.m[t],
+                          (p.in_c0[t] + static_cast<int32_t>(b0 + e) * p.in_c0_block_step + i * kTile) >> 2, 0, bar);
         }
       } else {
-        uint8_t* dst = s_data + stage * stage_bytes;
+        uint8_t* dst = s_raw + stage * stage_bytes;
         const int per_t = eb * kTile;
         for (int idx = tid; idx < k * per_t; idx += nthr) {
           const int t = idx / per_t, q = idx - t * per_t, e = q >> 8, x = q & (kTile - 1);
@@ -162,7 +177,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
           valid = valid < 0 ? 0 : (valid > S ? S : valid);
           uint8_t v = 0;
           if (e < nb && xg < valid) v = p.in_ptr[t][(b0 + e) * p.in_block_stride + xg];
-          dst[idx] = v;
+          dst[static_cast<uint32_t>(t) * group_bytes + e * rawp + x] = v;
         }
       }
     };
@@ -177,78 +192,66 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
       }
     } else {
       if (ntiles > 0) issue_tile(0, it % kStages);
-      if (ntiles > 1) issue_tile(1, (it + 1) % kStages);
       __syncthreads();
     }
-
-    // ---------------- HH window: packets [8i - rho, 8i + 8 - rho) clipped to [0, npk)
-    auto hh_window = [&](int i, uint32_t st_prev, uint32_t st_cur) {
-      if (!hh_live) return;
-      const uint8_t* base_prev = is_out ? s_par + ((i - 1) & 1) * par_bytes : s_data + st_prev * stage_bytes;
-      const uint8_t* base_cur = is_out ? s_par + (i & 1) * par_bytes : s_data + st_cur * stage_bytes;
-      const uint32_t a_prev = smem_u32(base_prev) + hh_rowoff + (8 - rho) * 32;
-      const uint32_t a_cur = smem_u32(base_cur) + hh_rowoff - rho * 32;
-      const int q0 = 8 * i - rho;
-      if (q0 >= 0 && q0 + 8 <= npk) {
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-          const uint32_t a = (j < 3 && rho > j) ? a_prev : a_cur;
-          const uint4 v = lds128(a + 32 * j);
-          hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
-        }
-      } else {
-#pragma unroll 1
-        for (int j = 0; j < 8; j++) {
-          const int q = q0 + j;
-          if (q < 0 || q >= npk) continue;
-          const uint32_t a = (rho > j) ? a_prev : a_cur;
-          const uint4 v = lds128(a + 32 * j);
-          hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
-        }
-      }
-    };
 
     // ---------------- main tile loop
     for (int i = 0; i < ntiles; i++) {
       const uint32_t st_cur = (it + i) % kStages;
-      const uint32_t st_prev = (it + i + kStages - 1) % kStages;
       if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[st_cur]), ((it + i) / kStages) & 1u);
 
-      // ---- GF step on tile i -> output tile (i & 1) in smem + global
-      if (r > 0) {
-        const uint8_t* din = s_data + st_cur * stage_bytes;
-        uint8_t* dpar = s_par + (i & 1) * par_bytes;
+      // ---- GF step on tile i: re-align, re-store, multiply, store
+      {
+        const uint8_t* din = s_raw + st_cur * stage_bytes;
         const int ncol = eb * (kTile / 8);
         for (int c = tid; c < ncol; c += nthr) {
           const int e = c >> 5, x8 = c & 31;
           const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
           const bool store_ok = e < nb && xg < S;
-          if constexpr (GF::kIsStatic) {
-            constexpr int K = GF::K, R = GF::R;
-            uint32_t lo[K], hi[K], olo[R], ohi[R];
-#pragma unroll
-            for (int t = 0; t < K; t++) {
-              const uint2 v = *reinterpret_cast<const uint2*>(din + (t * eb + e) * kTile + x8 * 8);
-              lo[t] = v.x; hi[t] = v.y;
+          uint8_t* crow = s_clean + static_cast<uint32_t>(e * k) * kRowPitch + x8 * 8;
+          uint8_t* prow = s_par + static_cast<uint32_t>(e * r) * kRowPitch + x8 * 8;
+          auto load_col = [&](int t) -> uint2 {
+            const uint8_t* row = din + static_cast<uint32_t>(t) * group_bytes + e * rawp;
+            if constexpr (REALIGN) {
+              const uint32_t a = p.in_align[t];
+              const uint32_t* w = reinterpret_cast<const uint32_t*>(row + ((a + x8 * 8) & ~3u));
+              const uint32_t sel = 0x3210u + 0x1111u * (a & 3u);
+              const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+              return make_uint2(prmt(w0, w1, sel), prmt(w1, w2, sel));
+            } else {
+              return *reinterpret_cast<const uint2*>(row + x8 * 8);
             }
-            GfStaticApply<typename GF::Mat>::run(lo, olo);
-            GfStaticApply<typename GF::Mat>::run(hi, ohi);
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-              const uint2 o = make_uint2(olo[j], ohi[j]);
-              *reinterpret_cast<uint2*>(dpar + (j * eb + e) * kTile + x8 * 8) = o;
-              if (store_ok) {
-                uint8_t* gp = p.out + ((b0 + e) * R + j) * p.out_pitch + xg;
-                if (xg + 8 <= S) {
-                  *reinterpret_cast<uint2*>(gp) = o;
-                } else {
-                  const uint64_t w = pack64(o.x, o.y);
-                  for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
-                }
+          };
+          auto store_out = [&](int j, uint2 o) {
+            *reinterpret_cast<uint2*>(prow + j * kRowPitch) = o;
+            if (store_ok) {
+              uint8_t* gp = p.out + ((b0 + e) * r + j) * p.out_pitch + xg;
+              if (xg + 8 <= S) {
+                *reinterpret_cast<uint2*>(gp) = o;
+              } else {
+                const uint64_t w = pack64(o.x, o.y);
+                for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
               }
             }
+          };
+          if constexpr (GF::kIsStatic) {
+            constexpr int K = GF::K, R = GF::R;
+            uint32_t lo[K], hi[K];
+#pragma unroll
+            for (int t = 0; t < K; t++) {
+              const uint2 v = load_col(t);
+              lo[t] = v.x; hi[t] = v.y;
+              *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
+            }
+            if constexpr (R > 0) {
+              uint32_t olo[R], ohi[R];
+              GfStaticApply<typename GF::Mat>::run(lo, olo);
+              GfStaticApply<typename GF::Mat>::run(hi, ohi);
+#pragma unroll
+              for (int j = 0; j < R; j++) store_out(j, make_uint2(olo[j], ohi[j]));
+            }
           } else {
-            for (int j0 = 0; j0 < r; j0 += kRChunk) {
+            for (int j0 = 0; j0 < (r > 0 ? r : 1); j0 += kRChunk) {
               uint32_t pl[kRChunk][8], ph[kRChunk][8];
 #pragma unroll
               for (int j = 0; j < kRChunk; j++)
@@ -256,7 +259,9 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
                 for (int b = 0; b < 8; b++) { pl[j][b] = 0u; ph[j][b] = 0u; }
 #pragma unroll 2
               for (int t = 0; t < k; t++) {
-                const uint2 v = *reinterpret_cast<const uint2*>(din + (t * eb + e) * kTile + x8 * 8);
+                const uint2 v = load_col(t);
+                if (j0 == 0) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
+                if (r == 0) continue;
                 const uint4* mk = reinterpret_cast<const uint4*>(s_masks + (t * rpad + j0) * 8);
 #pragma unroll
                 for (int j = 0; j < kRChunk; j++) {
@@ -280,48 +285,51 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
                   al = gf_xtime4(al) ^ pl[j][b];
                   ah = gf_xtime4(ah) ^ ph[j][b];
                 }
-                const uint2 o = make_uint2(al, ah);
-                *reinterpret_cast<uint2*>(dpar + ((j0 + j) * eb + e) * kTile + x8 * 8) = o;
-                if (store_ok) {
-                  uint8_t* gp = p.out + ((b0 + e) * r + (j0 + j)) * p.out_pitch + xg;
-                  if (xg + 8 <= S) {
-                    *reinterpret_cast<uint2*>(gp) = o;
-                  } else {
-                    const uint64_t w = pack64(o.x, o.y);
-                    for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
-                  }
-                }
+                store_out(j0 + j, make_uint2(al, ah));
               }
             }
           }
         }
       }
-      __syncthreads();  // (A) output tile i visible to the hash threads
+      __syncthreads();  // (A) aligned + output tiles complete; raw stage st_cur fully consumed
 
-      hh_window(i, st_prev, st_cur);
-
-      __syncthreads();  // (B) tile i-1 (input stage + output buffer) is now free
-      if (i + 2 < ntiles) {
+      if (i + kStages < ntiles || (!USE_TMA && i + 1 < ntiles)) {
         if constexpr (USE_TMA) {
           if (warp0) {
-            if (elect_one()) issue_tile(i + 2, (it + i + 2) % kStages);
+            if (elect_one()) issue_tile(i + kStages, st_cur);
             __syncwarp();
           }
         } else {
-          issue_tile(i + 2, (it + i + 2) % kStages);
+          issue_tile(i + 1, (it + i + 1) % kStages);  // visible after barrier (B)
         }
       }
+
+      // ---- HH step: packets [8i, 8i+8) of every stream
+      if (hh_live) {
+        const int q0 = 8 * i;
+        if (q0 + 8 <= npk) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            const uint4 v = lds128(hh_addr + 32 * j);
+            hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
+          }
+        } else {
+#pragma unroll 1
+          for (int j = 0; q0 + j < npk; j++) {
+            const uint4 v = lds128(hh_addr + 32 * j);
+            hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
+          }
+        }
+        if (i == ntiles - 1 && rem) {
+          const uint8_t* tail = hh_row + ((npk * 32) & (kTile - 1));
+          hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
+        }
+      }
+      __syncthreads();  // (B) aligned + output tiles may be overwritten
     }
 
-    // ---------------- drain the skewed packets, remainder bytes, finalisation
+    // ---------------- finalisation
     {
-      const uint32_t st_last = (it + (ntiles > 0 ? ntiles - 1 : 0)) % kStages;
-      if (ntiles > 0) hh_window(ntiles, st_last, st_last);
-      if (hh_live && rem) {
-        const uint8_t* base = is_out ? s_par + ((ntiles - 1) & 1) * par_bytes : s_data + st_last * stage_bytes;
-        const uint8_t* tail = base + (hh_rowoff - 16u * h) + ((npk * 32) & (kTile - 1));
-        hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
-      }
       uint64_t d0, d1;
       hh_finalize(hs, d0, d1);  // all threads of the warp take part in the shuffles
       if (hh_live) {
@@ -340,7 +348,6 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
         }
       }
     }
-    __syncthreads();  // stages are reused by the next group's prologue
     it += static_cast<uint32_t>(ntiles);
   }
 }

@@ -45,10 +45,27 @@ __device__ __forceinline__ void op(uint32_t& a, uint32_t& b, uint32_t c) {
     asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(a) : "r"(c));
     asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b) : "r"(a), "r"(c));
   }
-  if constexpr (OP == 12) {  // shared 128-bit load
+  if constexpr (OP == 12) {  // LOP3 with immediate + IMAD with immediate (fewer register reads)
+    asm volatile("lop3.b32 %0, %0, %1, 0x1d1d1d1d, 0x96;" : "+r"(a) : "r"(b));
+    asm volatile("mad.lo.u32 %0, %0, 3, %1;" : "+r"(b) : "r"(a));
+  }
+  if constexpr (OP == 13) {  // LOP3 : PRMT : IMAD 1:1:1
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("prmt.b32 %0, %0, %1, 0x5140;" : "+r"(b) : "r"(a));
+    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(a) : "r"(b), "r"(c));
+  }
+  if constexpr (OP == 14) {  // 2-register LOP3 (and) + 2-register add
+    asm volatile("and.b32 %0, %0, %1;" : "+r"(a) : "r"(b));
+    asm volatile("mad.lo.u32 %0, %0, 5, %1;" : "+r"(b) : "r"(a));
+  }
+  if constexpr (OP == 15) {  // LOP3 x3 + IMAD x1
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(b) : "r"(a), "r"(c));
+    asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(b), "r"(c));
+    asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(b) : "r"(a), "r"(c));
   }
 }
-template <int OP> constexpr int ops_per_call() { return (OP == 7 || OP == 9 || OP == 11) ? 2 : (OP == 8 ? 3 : (OP == 5 ? 2 : (OP == 10 ? 2 : 1))); }
+template <int OP> constexpr int ops_per_call() { return (OP == 7 || OP == 9 || OP == 11 || OP == 12 || OP == 14) ? 2 : ((OP == 8 || OP == 13) ? 3 : (OP == 15 ? 4 : (OP == 5 ? 2 : (OP == 10 ? 2 : 1)))); }
 
 template <int OP>
 __global__ void bench(uint32_t* out, long long* cycles, uint32_t seed) {
@@ -96,8 +113,8 @@ int main() {
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   int sms = p.multiProcessorCount;
   printf("device %s, %d SMs\n", p.name, sms);
-  for (int tpb : {256, 512, 1024}) {
-    int bps = 1024 / tpb * 1;
+  for (int tpb : {1024, 512}) {
+    int bps = 1;
     run<0>("LOP3", sms, tpb, bps);
     run<1>("PRMT", sms, tpb, bps);
     run<2>("IADD", sms, tpb, bps);
@@ -110,6 +127,10 @@ int main() {
     run<8>("LOP3:IMAD 2:1", sms, tpb, bps);
     run<9>("PRMT:LOP3 1:1", sms, tpb, bps);
     run<11>("MULHI:LOP3 1:1", sms, tpb, bps);
+    run<12>("LOP3imm:IMADimm 1:1", sms, tpb, bps);
+    run<13>("LOP3:PRMT:IMAD 1:1:1", sms, tpb, bps);
+    run<14>("AND2:IMADimm 1:1", sms, tpb, bps);
+    run<15>("LOP3:IMAD 3:1", sms, tpb, bps);
     printf("\n");
   }
   return 0;
