@@ -43,7 +43,13 @@ __device__ __forceinline__ uint32_t gf_xtime4(uint32_t a) {
   const uint32_t m = prmt(a, 0u, 0xba98u);
   return ((a & 0x7f7f7f7fu) << 1) ^ (m & 0x1d1d1d1du);
 #elif MEC_XTIME == 1
-  // high-half multiply folds (h>>7)*0x1d into one FMA-pipe instruction
+  // one ALU-pipe op (the AND); the msb extraction is an integer subtract and the reduction a
+  // high-half multiply, both on the FMA pipe which this kernel leaves mostly idle
+  const uint32_t t = a & 0x7f7f7f7fu;
+  uint32_t h;
+  asm("sub.u32 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(t));  // == a & 0x80808080 (kept as IADD on purpose)
+  return (t + t) ^ __umulhi(h, 0x1du << 25);
+#elif MEC_XTIME == 2
   const uint32_t h = a & 0x80808080u;
   return ((a ^ h) << 1) ^ __umulhi(h, 0x1du << 25);
 #else
@@ -118,8 +124,8 @@ __device__ __forceinline__ void hh_init(HHHalf& s, const uint64_t (&key)[4], int
   s.v1[0] = i1a ^ rot32(ka); s.v1[1] = i1b ^ rot32(kb);
 }
 
-// ZipperMergeAndAdd(v1 = hi lane, v0 = lo lane) -> (add1, add0); byte shuffles as PRMTs
-__device__ __forceinline__ void hh_zipper(uint64_t hi, uint64_t lo, uint64_t& add1, uint64_t& add0) {
+// ZipperMergeAndAdd(v1 = hi lane, v0 = lo lane): the two 64-bit addends; byte shuffles as PRMTs
+__device__ __forceinline__ void hh_zipper(uint64_t hi, uint64_t lo, uint64_t& z1, uint64_t& z0) {
   const uint32_t v0l = static_cast<uint32_t>(lo), v0h = static_cast<uint32_t>(lo >> 32);
   const uint32_t v1l = static_cast<uint32_t>(hi), v1h = static_cast<uint32_t>(hi >> 32);
   // add0 += [v0.b3, v1.b4, v0.b2, v0.b5 | v1.b6, v0.b1, v1.b7, v0.b0]
@@ -130,21 +136,30 @@ __device__ __forceinline__ void hh_zipper(uint64_t hi, uint64_t lo, uint64_t& ad
   const uint32_t t1 = prmt(v1l, v1h, 0x5203u);
   const uint32_t a1l = prmt(t1, v0h, 0x3240u);
   const uint32_t a1h = prmt(v1l, v0h, 0x7061u);
-  add0 += pack64(a0l, a0h);
-  add1 += pack64(a1l, a1h);
+  z0 = pack64(a0l, a0h);
+  z1 = pack64(a1l, a1h);
 }
 
 __device__ __forceinline__ void hh_update(HHHalf& s, uint64_t a0, uint64_t a1) {
   const uint64_t a[2] = {a0, a1};
+  uint64_t m1old[2];
 #pragma unroll
   for (int i = 0; i < 2; i++) {
     s.v1[i] += s.m0[i] + a[i];
     s.m0[i] ^= static_cast<uint64_t>(static_cast<uint32_t>(s.v1[i])) * static_cast<uint32_t>(s.v0[i] >> 32);
-    s.v0[i] += s.m1[i];
-    s.m1[i] ^= static_cast<uint64_t>(static_cast<uint32_t>(s.v0[i])) * static_cast<uint32_t>(s.v1[i] >> 32);
+    // only the low word of (v0 += mul1) feeds the multiply; the full 64-bit add is merged with the
+    // zipper addend below into one 3-input carry chain
+    m1old[i] = s.m1[i];
+    const uint32_t v0lo = static_cast<uint32_t>(s.v0[i]) + static_cast<uint32_t>(m1old[i]);
+    s.m1[i] ^= static_cast<uint64_t>(v0lo) * static_cast<uint32_t>(s.v1[i] >> 32);
   }
-  hh_zipper(s.v1[1], s.v1[0], s.v0[1], s.v0[0]);
-  hh_zipper(s.v0[1], s.v0[0], s.v1[1], s.v1[0]);
+  uint64_t z1, z0;
+  hh_zipper(s.v1[1], s.v1[0], z1, z0);
+  s.v0[0] = s.v0[0] + m1old[0] + z0;
+  s.v0[1] = s.v0[1] + m1old[1] + z1;
+  hh_zipper(s.v0[1], s.v0[0], z1, z0);
+  s.v1[0] += z0;
+  s.v1[1] += z1;
 }
 
 // byte `pos` (0..31) of the padded remainder packet for a tail of n (1..31) bytes

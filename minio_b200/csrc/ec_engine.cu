@@ -28,21 +28,29 @@ void DevBuf::release() {
 // (k, m) pairs with compile-time specialised GF code.  MinIO's default parity for a 16-drive set
 // is EC:4 => RS(12,4) (internal/config/storageclass/storage-class.go:355); the others are the
 // BASELINE configs and common set sizes.
-#define MEC_STATIC_CONFIGS(X) X(12, 4) X(4, 2) X(16, 4) X(8, 8) X(8, 4) X(6, 2) X(2, 2)
+// X(K, M, S mod 16 for 1 MiB blocks)
+#define MEC_STATIC_CONFIGS(X) X(12, 4, 6) X(4, 2, 0) X(16, 4, 0) X(8, 8, 0) X(8, 4, 0) X(6, 2, 11) X(2, 2, 0)
 
 using KernelFn = void (*)(const FusedParams, const TmaMaps);
+constexpr int kStaticEb = 4;  // erasure blocks per CTA of the compile-time specialised kernels
 
 struct StaticEntry {
-  int k, m;
-  KernelFn fn[3];  // indexed by loader: 0 byte-wise, 1 TMA aligned, 2 TMA + re-align
+  int k, m, sm16;
+  KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb
+  KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb
+  KernelFn runtime;   // TMA, any alignment (per-row table), runtime eb
+  KernelFn bytewise;  // byte-wise loader, runtime eb
 };
 static const StaticEntry kStaticTable[] = {
-#define X(K, M) {K, M, {fused_rs_hh_kernel<GfStatic<K, M>, 0>, fused_rs_hh_kernel<GfStatic<K, M>, 1>, fused_rs_hh_kernel<GfStatic<K, M>, 2>}},
+#define X(K, M, A)                                                                                          \
+  {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb>, fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb>, \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0>},
     MEC_STATIC_CONFIGS(X)
 #undef X
 };
-static const KernelFn kDynamicFn[3] = {fused_rs_hh_kernel<GfDynamic, 0>, fused_rs_hh_kernel<GfDynamic, 1>,
-                                       fused_rs_hh_kernel<GfDynamic, 2>};
+static const KernelFn kDynAligned = fused_rs_hh_kernel<GfDynamic, true, 0, 0>;
+static const KernelFn kDynRuntime = fused_rs_hh_kernel<GfDynamic, true, kAlignRuntime, 0>;
+static const KernelFn kDynBytewise = fused_rs_hh_kernel<GfDynamic, false, 0, 0>;
 
 Engine::Engine(int device) : device_(device) {}
 Engine::~Engine() {}
@@ -122,7 +130,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
 
   // ---- erasure blocks per CTA and block size
   int eb = opt.eb > 0 ? opt.eb : (128 / (2 * n) > 0 ? 128 / (2 * n) : 1);
-  if (eb > d.nblocks) eb = static_cast<int>(d.nblocks);
+  if (opt.eb <= 0 && d.static_encode && d.contiguous) eb = kStaticEb;  // OOB blocks of a partial group read as zeros
+  else if (eb > d.nblocks) eb = static_cast<int>(d.nblocks);
   while (eb > 1 && 2 * n * eb > 256) eb--;
   if (eb > 255) eb = 255;
   int threads = (2 * n * eb + 31) / 32 * 32;
@@ -130,7 +139,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
 
   // ---- static / dynamic GF
   const StaticEntry* se = nullptr;
-  if (d.static_encode && !opt.force_dynamic)
+  if (d.static_encode && d.contiguous && !opt.force_dynamic)
     for (const auto& ent : kStaticTable)
       if (ent.k == d.k && ent.m == d.r) se = &ent;
   if (!se) {
@@ -196,10 +205,19 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       }
     }
   }
-  const int loader = !use_tma ? 0 : (any_misaligned ? 2 : 1);
   if (!use_tma) p.tma_mode = kLoadBytewise;
+  if (!use_tma) p.raw_pitch = kRawRow;
 
-  KernelFn fn = se ? se->fn[loader] : kDynamicFn[loader];
+  KernelFn fn;
+  if (se) {
+    const int sm16 = static_cast<int>(d.S & 15);
+    if (!use_tma) fn = se->bytewise;
+    else if (eb == kStaticEb && sm16 == se->sm16) fn = se->fast;
+    else if (eb == kStaticEb && sm16 == 0) fn = se->aligned;
+    else fn = se->runtime;
+  } else {
+    fn = !use_tma ? kDynBytewise : (any_misaligned ? kDynRuntime : kDynAligned);
+  }
   const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr);
   if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;
   MEC_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,

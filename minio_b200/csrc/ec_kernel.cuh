@@ -11,13 +11,15 @@
 //   CTA      = `eb` erasure blocks, blockDim = 2*(k+r)*eb rounded up to a warp multiple
 //   tile     = 256 bytes of every shard.  Shards start at arbitrary byte offsets of the object
 //              (S = ceil(blockSize/k) is 87382 for RS(12,4)@1MiB) but TMA boxes must start on 16-byte
-//              boundaries, so each row is fetched as the 272-byte 16B-aligned superset into a 2-deep
-//              ring (cp.async.bulk.tensor, u32 elements; Split's zero padding = TMA OOB fill)
-//   GF step  = each thread owns an 8-byte column: per row 3 LDS.32 + 2 PRMT re-align the bytes in
-//              registers (or one LDS.64 when every row is 16B-aligned), the aligned column is
-//              re-stored for the hash threads, r outputs are computed -> STS.64 + STG.64
+//              boundaries, so each row is fetched as its 272-byte 16B-aligned superset ("raw" tile,
+//              cp.async.bulk.tensor with u32 elements; Split's zero padding = TMA out-of-bounds fill)
+//   GF step  = each thread owns an 8-byte column: rows are re-aligned in registers (PRMT with
+//              compile-time selectors when S mod 16 is a template constant), re-stored into the
+//              "aligned" tile for the hash threads, and multiplied -> r outputs -> STS.64 + STG.64
 //   HH step  = two threads per shard stream (64-bit lanes {0,1} / {2,3}); rows of the aligned tile
-//              have a 288-byte pitch so the four streams of a quarter-warp hit disjoint banks
+//              have a 288-byte pitch so the four streams of a quarter-warp hit disjoint banks.
+//   pipeline = raw tile i+1 is in flight (TMA) while the hash threads chew on aligned tile i; two
+//              CTA barriers per tile, hidden by 6-7 resident CTAs per SM.
 #pragma once
 #include "ec_device.cuh"
 
@@ -26,11 +28,11 @@ namespace mec {
 constexpr int kTile = 256;       // bytes of one shard per tile
 constexpr int kRawRow = 272;     // 16B-aligned superset of a tile row
 constexpr int kRowPitch = 288;   // pitch of the aligned data / output tiles (bank skew of 32 B)
-constexpr int kStages = 2;       // raw tile ring depth
 constexpr int kMaxK = 32;        // inputs supported by the GPU path
 constexpr int kMaxR = 16;        // outputs supported by the GPU path
 constexpr int kMaxMaps = 16;     // tensor maps carried in kernel params
 constexpr int kRChunk = 4;       // rows per pass in the runtime-matrix GF step
+constexpr int kAlignRuntime = -1;
 
 enum LoaderMode : int { kLoadBytewise = 0, kLoadTmaBlocks2D = 1, kLoadTmaPerInput = 2 };
 
@@ -40,7 +42,7 @@ struct alignas(64) TmaMaps {
 
 struct FusedParams {
   int k, r, eb, tma_mode;
-  int raw_pitch;                   // bytes between erasure blocks inside a raw row group (272, or 384 when every row is its own TMA box)
+  int raw_pitch;                   // bytes between erasure blocks inside a raw row group (272; 384 when every row is its own TMA box)
   int64_t nblocks;
   int32_t S;                       // shard bytes per erasure block
   int32_t in_c0_block_step;        // kLoadTmaPerInput: bytes between blocks in an input stream (multiple of 16)
@@ -74,8 +76,8 @@ struct GfDynamic {
 __host__ __device__ inline uint32_t raw_group_bytes(int eb, int raw_pitch) { return (static_cast<uint32_t>(eb) * raw_pitch + 127u) & ~127u; }
 
 __host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, int raw_pitch, bool dynamic_gf) {
-  uint32_t b = 128 + 128;  // alignment slack + barriers
-  b += static_cast<uint32_t>(kStages) * k * raw_group_bytes(eb, raw_pitch);
+  uint32_t b = 128 + 128;  // alignment slack + barrier
+  b += static_cast<uint32_t>(k) * raw_group_bytes(eb, raw_pitch);
   b += static_cast<uint32_t>(k + (r > 0 ? r : 0)) * eb * kRowPitch;
   if (dynamic_gf) b += static_cast<uint32_t>(k) * ((r + kRChunk - 1) / kRChunk) * kRChunk * 8 * 4;
   return b;
@@ -85,26 +87,48 @@ __host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, int r
 #define MEC_MIN_BLOCKS 3
 #endif
 
-// LOADER: 0 = byte-wise fallback, 1 = TMA with every row 16B-aligned, 2 = TMA + register re-alignment
-template <class GF, int LOADER>
+// one 8-byte column of raw row `row` whose logical byte 0 sits `A` bytes into the row
+template <int A>
+__device__ __forceinline__ uint2 load_col_ct(const uint8_t* row) {
+  constexpr int base = A & ~3, sh = A & 3;
+  if constexpr (sh == 0 && (base & 7) == 0) {
+    return *reinterpret_cast<const uint2*>(row + base);
+  } else if constexpr (sh == 0) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row + base);
+    return make_uint2(w[0], w[1]);
+  } else {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row + base);
+    constexpr uint32_t sel = 0x3210u + 0x1111u * sh;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return make_uint2(prmt(w0, w1, sel), prmt(w1, w2, sel));
+  }
+}
+__device__ __forceinline__ uint2 load_col_rt(const uint8_t* row, uint32_t a) {
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(row + (a & ~3u));
+  const uint32_t sel = 0x3210u + 0x1111u * (a & 3u);
+  const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+  return make_uint2(prmt(w0, w1, sel), prmt(w1, w2, sel));
+}
+
+// USE_TMA: tile loader.  ALIGN: S mod 16 of a contiguous (Split) input when known at compile time
+// (0 = every row 16B-aligned), kAlignRuntime = per-row table in the params.  EB_T: erasure blocks
+// per CTA when fixed at compile time (0 = runtime).
+template <class GF, bool USE_TMA, int ALIGN, int EB_T>
 __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
-  constexpr bool USE_TMA = LOADER != 0;
-  constexpr bool REALIGN = LOADER == 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int k = GF::kIsStatic ? GF::K : p.k;
   const int r = GF::kIsStatic ? GF::R : p.r;
-  const int eb = p.eb;
+  const int eb = EB_T > 0 ? EB_T : p.eb;
   const int nstreams = k + r;
   const int tid = threadIdx.x, nthr = blockDim.x;
   const bool warp0 = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;  // provably warp-uniform
-  const uint32_t rawp = static_cast<uint32_t>(p.raw_pitch);
-  const uint32_t group_bytes = raw_group_bytes(eb, p.raw_pitch);
-  const uint32_t stage_bytes = static_cast<uint32_t>(k) * group_bytes;
+  const uint32_t rawp = EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch);
+  const uint32_t group_bytes = raw_group_bytes(eb, static_cast<int>(rawp));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint8_t* s_raw = smem + 128;
-  uint8_t* s_clean = s_raw + kStages * stage_bytes;                          // [eb][k][kRowPitch]
+  uint8_t* s_raw = smem + 128;                                               // [k][group]
+  uint8_t* s_clean = s_raw + static_cast<uint32_t>(k) * group_bytes;         // [eb][k][kRowPitch]
   uint8_t* s_par = s_clean + static_cast<uint32_t>(k) * eb * kRowPitch;      // [eb][r][kRowPitch]
   uint32_t* s_masks = reinterpret_cast<uint32_t*>(s_par + static_cast<uint32_t>(r) * eb * kRowPitch);
   const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
@@ -115,7 +139,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
 
   if constexpr (USE_TMA) {
     if (tid == 0) {
-      for (int s = 0; s < kStages; s++) mbar_init(smem_u32(&bars[s]), 1);
+      mbar_init(smem_u32(&bars[0]), 1);
       fence_barrier_init();
     }
   }
@@ -139,8 +163,11 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
                                  : s_clean + static_cast<uint32_t>(e_hh * k + srow) * kRowPitch;
   const uint32_t hh_addr = smem_u32(hh_row) + 16u * h;
 
+  // ---- GF thread identity: one 8-byte column (threads beyond eb*32 columns idle in the GF step)
+  const int ncol = eb * (kTile / 8);
+
   const int64_t ngroups = (p.nblocks + eb - 1) / eb;
-  uint32_t it = 0;  // running tile counter (stage / mbarrier phase bookkeeping)
+  uint32_t it = 0;  // running tile counter (mbarrier phase bookkeeping)
 
   for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
     const int64_t b0 = g * eb;
@@ -150,11 +177,11 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
     HHHalf hs;
     hh_init(hs, p.key, h);
 
-    // ---------------- tile loaders
-    auto issue_tile = [&](int i, uint32_t stage) {  // TMA: one elected lane; byte-wise: all threads
+    // ---------------- tile loader (raw tile is single-buffered: it is free as soon as GF(i) is done)
+    auto issue_tile = [&](int i) {  // TMA: one elected lane; byte-wise: all threads
       if constexpr (USE_TMA) {
-        const uint32_t bar = smem_u32(&bars[stage]);
-        const uint32_t dst0 = smem_u32(s_raw + stage * stage_bytes);
+        const uint32_t bar = smem_u32(&bars[0]);
+        const uint32_t dst0 = smem_u32(s_raw);
         if (p.tma_mode == kLoadTmaBlocks2D) {
           mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
           for (int t = 0; t < k; t++)
@@ -168,7 +195,6 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
                           (p.in_c0[t] + static_cast<int32_t>(b0 + e) * p.in_c0_block_step + i * kTile) >> 2, 0, bar);
         }
       } else {
-        uint8_t* dst = s_raw + stage * stage_bytes;
         const int per_t = eb * kTile;
         for (int idx = tid; idx < k * per_t; idx += nthr) {
           const int t = idx / per_t, q = idx - t * per_t, e = q >> 8, x = q & (kTile - 1);
@@ -177,130 +203,115 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
           valid = valid < 0 ? 0 : (valid > S ? S : valid);
           uint8_t v = 0;
           if (e < nb && xg < valid) v = p.in_ptr[t][(b0 + e) * p.in_block_stride + xg];
-          dst[static_cast<uint32_t>(t) * group_bytes + e * rawp + x] = v;
+          s_raw[static_cast<uint32_t>(t) * group_bytes + e * rawp + x] = v;
         }
       }
     };
 
     if constexpr (USE_TMA) {
       if (warp0) {
-        if (elect_one()) {
-          if (ntiles > 0) issue_tile(0, it % kStages);
-          if (ntiles > 1) issue_tile(1, (it + 1) % kStages);
-        }
+        if (elect_one() && ntiles > 0) issue_tile(0);
         __syncwarp();
       }
     } else {
-      if (ntiles > 0) issue_tile(0, it % kStages);
+      if (ntiles > 0) issue_tile(0);
       __syncthreads();
     }
 
     // ---------------- main tile loop
     for (int i = 0; i < ntiles; i++) {
-      const uint32_t st_cur = (it + i) % kStages;
-      if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[st_cur]), ((it + i) / kStages) & 1u);
+      if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
 
       // ---- GF step on tile i: re-align, re-store, multiply, store
-      {
-        const uint8_t* din = s_raw + st_cur * stage_bytes;
-        const int ncol = eb * (kTile / 8);
-        for (int c = tid; c < ncol; c += nthr) {
-          const int e = c >> 5, x8 = c & 31;
-          const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
-          const bool store_ok = e < nb && xg < S;
-          uint8_t* crow = s_clean + static_cast<uint32_t>(e * k) * kRowPitch + x8 * 8;
-          uint8_t* prow = s_par + static_cast<uint32_t>(e * r) * kRowPitch + x8 * 8;
-          auto load_col = [&](int t) -> uint2 {
-            const uint8_t* row = din + static_cast<uint32_t>(t) * group_bytes + e * rawp;
-            if constexpr (REALIGN) {
-              const uint32_t a = p.in_align[t];
-              const uint32_t* w = reinterpret_cast<const uint32_t*>(row + ((a + x8 * 8) & ~3u));
-              const uint32_t sel = 0x3210u + 0x1111u * (a & 3u);
-              const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-              return make_uint2(prmt(w0, w1, sel), prmt(w1, w2, sel));
-            } else {
-              return *reinterpret_cast<const uint2*>(row + x8 * 8);
-            }
-          };
-          auto store_out = [&](int j, uint2 o) {
-            *reinterpret_cast<uint2*>(prow + j * kRowPitch) = o;
-            if (store_ok) {
-              uint8_t* gp = p.out + ((b0 + e) * r + j) * p.out_pitch + xg;
-              if (xg + 8 <= S) {
-                *reinterpret_cast<uint2*>(gp) = o;
-              } else {
-                const uint64_t w = pack64(o.x, o.y);
-                for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
-              }
-            }
-          };
-          if constexpr (GF::kIsStatic) {
-            constexpr int K = GF::K, R = GF::R;
-            uint32_t lo[K], hi[K];
+      for (int c = tid; c < ncol; c += nthr) {
+        const int e = c >> 5, x8 = c & 31;
+        const uint8_t* rcol = s_raw + e * rawp + x8 * 8;
+        uint8_t* crow = s_clean + static_cast<uint32_t>(e * k) * kRowPitch + x8 * 8;
+        uint8_t* prow = s_par + static_cast<uint32_t>(e * r) * kRowPitch + x8 * 8;
+        const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
+        uint8_t* gout = p.out + (b0 + e) * r * p.out_pitch + xg;
+        const bool full = e < nb && xg + 8 <= S;
+        const bool part = e < nb && xg < S && !full;
+        auto store_out = [&](int j, uint2 o) {
+          *reinterpret_cast<uint2*>(prow + j * kRowPitch) = o;
+          uint8_t* gp = gout + j * p.out_pitch;
+          if (full) {
+            *reinterpret_cast<uint2*>(gp) = o;
+          } else if (part) {
+            const uint64_t w = pack64(o.x, o.y);
+            for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
+          }
+        };
+        if constexpr (GF::kIsStatic) {
+          constexpr int K = GF::K, R = GF::R;
+          uint32_t lo[K], hi[K];
+          static_for<K>([&](auto t_) {
+            constexpr int t = decltype(t_)::value;
+            uint2 v;
+            if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
+            else v = load_col_ct<(t * ALIGN) & 15>(rcol + t * group_bytes);
+            lo[t] = v.x; hi[t] = v.y;
+            *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
+          });
+          if constexpr (R > 0) {
+            uint32_t olo[R], ohi[R];
+            GfStaticApply<typename GF::Mat>::run(lo, olo);
+            GfStaticApply<typename GF::Mat>::run(hi, ohi);
 #pragma unroll
-            for (int t = 0; t < K; t++) {
-              const uint2 v = load_col(t);
-              lo[t] = v.x; hi[t] = v.y;
-              *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
-            }
-            if constexpr (R > 0) {
-              uint32_t olo[R], ohi[R];
-              GfStaticApply<typename GF::Mat>::run(lo, olo);
-              GfStaticApply<typename GF::Mat>::run(hi, ohi);
+            for (int j = 0; j < R; j++) store_out(j, make_uint2(olo[j], ohi[j]));
+          }
+        } else {
+          for (int j0 = 0; j0 < (r > 0 ? r : 1); j0 += kRChunk) {
+            uint32_t pl[kRChunk][8], ph[kRChunk][8];
 #pragma unroll
-              for (int j = 0; j < R; j++) store_out(j, make_uint2(olo[j], ohi[j]));
-            }
-          } else {
-            for (int j0 = 0; j0 < (r > 0 ? r : 1); j0 += kRChunk) {
-              uint32_t pl[kRChunk][8], ph[kRChunk][8];
+            for (int j = 0; j < kRChunk; j++)
 #pragma unroll
-              for (int j = 0; j < kRChunk; j++)
-#pragma unroll
-                for (int b = 0; b < 8; b++) { pl[j][b] = 0u; ph[j][b] = 0u; }
+              for (int b = 0; b < 8; b++) { pl[j][b] = 0u; ph[j][b] = 0u; }
 #pragma unroll 2
-              for (int t = 0; t < k; t++) {
-                const uint2 v = load_col(t);
-                if (j0 == 0) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
-                if (r == 0) continue;
-                const uint4* mk = reinterpret_cast<const uint4*>(s_masks + (t * rpad + j0) * 8);
-#pragma unroll
-                for (int j = 0; j < kRChunk; j++) {
-                  const uint4 m0 = mk[2 * j], m1 = mk[2 * j + 1];
-                  pl[j][0] ^= v.x & m0.x; ph[j][0] ^= v.y & m0.x;
-                  pl[j][1] ^= v.x & m0.y; ph[j][1] ^= v.y & m0.y;
-                  pl[j][2] ^= v.x & m0.z; ph[j][2] ^= v.y & m0.z;
-                  pl[j][3] ^= v.x & m0.w; ph[j][3] ^= v.y & m0.w;
-                  pl[j][4] ^= v.x & m1.x; ph[j][4] ^= v.y & m1.x;
-                  pl[j][5] ^= v.x & m1.y; ph[j][5] ^= v.y & m1.y;
-                  pl[j][6] ^= v.x & m1.z; ph[j][6] ^= v.y & m1.z;
-                  pl[j][7] ^= v.x & m1.w; ph[j][7] ^= v.y & m1.w;
-                }
-              }
+            for (int t = 0; t < k; t++) {
+              uint2 v;
+              if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
+              else v = *reinterpret_cast<const uint2*>(rcol + t * group_bytes);
+              if (j0 == 0) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
+              if (r == 0) continue;
+              const uint4* mk = reinterpret_cast<const uint4*>(s_masks + (t * rpad + j0) * 8);
 #pragma unroll
               for (int j = 0; j < kRChunk; j++) {
-                if (j0 + j >= r) break;
-                uint32_t al = pl[j][7], ah = ph[j][7];
-#pragma unroll
-                for (int b = 6; b >= 0; b--) {
-                  al = gf_xtime4(al) ^ pl[j][b];
-                  ah = gf_xtime4(ah) ^ ph[j][b];
-                }
-                store_out(j0 + j, make_uint2(al, ah));
+                const uint4 m0 = mk[2 * j], m1 = mk[2 * j + 1];
+                pl[j][0] ^= v.x & m0.x; ph[j][0] ^= v.y & m0.x;
+                pl[j][1] ^= v.x & m0.y; ph[j][1] ^= v.y & m0.y;
+                pl[j][2] ^= v.x & m0.z; ph[j][2] ^= v.y & m0.z;
+                pl[j][3] ^= v.x & m0.w; ph[j][3] ^= v.y & m0.w;
+                pl[j][4] ^= v.x & m1.x; ph[j][4] ^= v.y & m1.x;
+                pl[j][5] ^= v.x & m1.y; ph[j][5] ^= v.y & m1.y;
+                pl[j][6] ^= v.x & m1.z; ph[j][6] ^= v.y & m1.z;
+                pl[j][7] ^= v.x & m1.w; ph[j][7] ^= v.y & m1.w;
               }
+            }
+#pragma unroll
+            for (int j = 0; j < kRChunk; j++) {
+              if (j0 + j >= r) break;
+              uint32_t al = pl[j][7], ah = ph[j][7];
+#pragma unroll
+              for (int b = 6; b >= 0; b--) {
+                al = gf_xtime4(al) ^ pl[j][b];
+                ah = gf_xtime4(ah) ^ ph[j][b];
+              }
+              store_out(j0 + j, make_uint2(al, ah));
             }
           }
         }
       }
-      __syncthreads();  // (A) aligned + output tiles complete; raw stage st_cur fully consumed
+      __syncthreads();  // (A) aligned + output tiles complete; raw tile fully consumed
 
-      if (i + kStages < ntiles || (!USE_TMA && i + 1 < ntiles)) {
+      if (i + 1 < ntiles) {  // refill the raw tile while the hash threads work on the aligned one
         if constexpr (USE_TMA) {
           if (warp0) {
-            if (elect_one()) issue_tile(i + kStages, st_cur);
+            if (elect_one()) issue_tile(i + 1);
             __syncwarp();
           }
         } else {
-          issue_tile(i + 1, (it + i + 1) % kStages);  // visible after barrier (B)
+          issue_tile(i + 1);  // visible after barrier (B)
         }
       }
 
