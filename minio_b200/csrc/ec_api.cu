@@ -134,6 +134,7 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else if (!strcmp(name, "force_bytewise")) c->opt.force_bytewise = static_cast<int>(v);
   else if (!strcmp(name, "force_dynamic")) c->opt.force_dynamic = static_cast<int>(v);
   else if (!strcmp(name, "grid_mult")) c->opt.grid_mult = static_cast<int>(v);
+  else if (!strcmp(name, "no_auto")) c->opt.no_auto = static_cast<int>(v);
   else if (!strcmp(name, "chunk_blocks")) c->opt.chunk_blocks = v;
   else return MEC_ERR_INVALID_ARGUMENT;
   return MEC_OK;

@@ -36,21 +36,23 @@ constexpr int kStaticEb = 4;  // erasure blocks per CTA of the compile-time spec
 
 struct StaticEntry {
   int k, m, sm16;
-  KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb
-  KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb
+  KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb (warp-autonomous when k + m == 16)
+  KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb (warp-autonomous when k + m == 16)
   KernelFn runtime;   // TMA, any alignment (per-row table), runtime eb
   KernelFn bytewise;  // byte-wise loader, runtime eb
 };
 static const StaticEntry kStaticTable[] = {
-#define X(K, M, A)                                                                                          \
-  {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb>, fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb>, \
-   fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0>},
+#define X(K, M, A)                                                                                      \
+  {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16)>,                       \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16)>,                                \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0, false>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0, false>},
     MEC_STATIC_CONFIGS(X)
 #undef X
 };
-static const KernelFn kDynAligned = fused_rs_hh_kernel<GfDynamic, true, 0, 0>;
-static const KernelFn kDynRuntime = fused_rs_hh_kernel<GfDynamic, true, kAlignRuntime, 0>;
-static const KernelFn kDynBytewise = fused_rs_hh_kernel<GfDynamic, false, 0, 0>;
+static const KernelFn kDynAligned = fused_rs_hh_kernel<GfDynamic, true, 0, 0, false>;
+static const KernelFn kDynAlignedAuto = fused_rs_hh_kernel<GfDynamic, true, 0, 0, true>;
+static const KernelFn kDynRuntime = fused_rs_hh_kernel<GfDynamic, true, kAlignRuntime, 0, false>;
+static const KernelFn kDynBytewise = fused_rs_hh_kernel<GfDynamic, false, 0, 0, false>;
 
 Engine::Engine(int device) : device_(device) {}
 Engine::~Engine() {}
@@ -216,7 +218,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     else if (eb == kStaticEb && sm16 == 0) fn = se->aligned;
     else fn = se->runtime;
   } else {
-    fn = !use_tma ? kDynBytewise : (any_misaligned ? kDynRuntime : kDynAligned);
+    const bool autonomous = (d.k + d.r == 16) && d.digests != nullptr && threads == 32 * eb && !opt.no_auto;
+    fn = !use_tma ? kDynBytewise : (any_misaligned ? kDynRuntime : (autonomous ? kDynAlignedAuto : kDynAligned));
   }
   const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr);
   if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;

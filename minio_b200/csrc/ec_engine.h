@@ -51,6 +51,7 @@ struct EngineOptions {
   int force_bytewise = 0;  // 1: never use TMA
   int force_dynamic = 0;   // 1: never use the compile-time specialised GF kernels
   int grid_mult = 0;       // CTAs per SM (0 = occupancy)
+  int no_auto = 0;         // 1: never use the warp-autonomous pipeline
   int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
 };
 

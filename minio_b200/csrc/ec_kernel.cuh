@@ -112,8 +112,11 @@ __device__ __forceinline__ uint2 load_col_rt(const uint8_t* row, uint32_t a) {
 
 // USE_TMA: tile loader.  ALIGN: S mod 16 of a contiguous (Split) input when known at compile time
 // (0 = every row 16B-aligned), kAlignRuntime = per-row table in the params.  EB_T: erasure blocks
-// per CTA when fixed at compile time (0 = runtime).
-template <class GF, bool USE_TMA, int ALIGN, int EB_T>
+// per CTA when fixed at compile time (0 = runtime).  AUTO: k + r == 16, i.e. one warp owns exactly
+// one erasure block (32 columns, 16 streams x 2 hash threads): the GF -> HH hand-off is then
+// warp-local (__syncwarp) and the only CTA-wide event is "raw tile consumed", tracked by an arrival
+// counter whose last arriver issues the next TMA batch — no __syncthreads in the steady state.
+template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO>
 __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
   extern __shared__ uint8_t smem_raw[];
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
   const uint32_t rawp = EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch);
   const uint32_t group_bytes = raw_group_bytes(eb, static_cast<int>(rawp));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint32_t* s_arrive = reinterpret_cast<uint32_t*>(smem + 64);
   uint8_t* s_raw = smem + 128;                                               // [k][group]
   uint8_t* s_clean = s_raw + static_cast<uint32_t>(k) * group_bytes;         // [eb][k][kRowPitch]
   uint8_t* s_par = s_clean + static_cast<uint32_t>(k) * eb * kRowPitch;      // [eb][r][kRowPitch]
@@ -141,6 +145,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
     if (tid == 0) {
       mbar_init(smem_u32(&bars[0]), 1);
       fence_barrier_init();
+      *s_arrive = 0;
     }
   }
   if constexpr (!GF::kIsStatic) {
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
     hh_init(hs, p.key, h);
 
     // ---------------- tile loader (raw tile is single-buffered: it is free as soon as GF(i) is done)
-    auto issue_tile = [&](int i) {  // TMA: one elected lane; byte-wise: all threads
+    auto issue_tile_at = [&](int i, int64_t b0, int nb) {  // TMA: one elected lane; byte-wise: all threads
       if constexpr (USE_TMA) {
         const uint32_t bar = smem_u32(&bars[0]);
         const uint32_t dst0 = smem_u32(s_raw);
@@ -207,9 +212,11 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
         }
       }
     };
+    auto issue_tile = [&](int i) { issue_tile_at(i, b0, nb); };
 
     if constexpr (USE_TMA) {
-      if (warp0) {
+      // AUTO: later groups are pre-issued by the last arriver of the previous group's final tile
+      if (warp0 && (!AUTO || g == static_cast<int64_t>(blockIdx.x))) {
         if (elect_one() && ntiles > 0) issue_tile(0);
         __syncwarp();
       }
@@ -302,16 +309,33 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
           }
         }
       }
-      __syncthreads();  // (A) aligned + output tiles complete; raw tile fully consumed
-
-      if (i + 1 < ntiles) {  // refill the raw tile while the hash threads work on the aligned one
-        if constexpr (USE_TMA) {
-          if (warp0) {
+      if constexpr (AUTO && USE_TMA) {
+        __syncwarp();  // (A) this warp's aligned + output rows are complete
+        uint32_t last = 0;
+        if ((tid & 31) == 0) last = (atomicAdd(s_arrive, 1u) % static_cast<uint32_t>(nthr >> 5)) == static_cast<uint32_t>((nthr >> 5) - 1);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {  // every warp of the CTA has consumed the raw tile: refill it
+          if (i + 1 < ntiles) {
             if (elect_one()) issue_tile(i + 1);
-            __syncwarp();
+          } else if (g + gridDim.x < ngroups) {
+            if (elect_one()) {  // first tile of this CTA's next group
+              const int64_t b0n = (g + gridDim.x) * eb;
+              issue_tile_at(0, b0n, (p.nblocks - b0n) < eb ? static_cast<int>(p.nblocks - b0n) : eb);
+            }
           }
-        } else {
-          issue_tile(i + 1);  // visible after barrier (B)
+          __syncwarp();
+        }
+      } else {
+        __syncthreads();  // (A) aligned + output tiles complete; raw tile fully consumed
+        if (i + 1 < ntiles) {  // refill the raw tile while the hash threads work on the aligned one
+          if constexpr (USE_TMA) {
+            if (warp0) {
+              if (elect_one()) issue_tile(i + 1);
+              __syncwarp();
+            }
+          } else {
+            issue_tile(i + 1);  // visible after barrier (B)
+          }
         }
       }
 
@@ -336,7 +360,8 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
           hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
         }
       }
-      __syncthreads();  // (B) aligned + output tiles may be overwritten
+      if constexpr (AUTO && USE_TMA) __syncwarp();  // (B) this warp's rows may be overwritten
+      else __syncthreads();                          // (B) aligned + output tiles may be overwritten
     }
 
     // ---------------- finalisation
