@@ -230,6 +230,22 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
       if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
 
       // ---- GF step on tile i: re-align, re-store, multiply, store
+      auto raw_consumed = [&]() {  // AUTO: count this warp's arrival; the last arriver refills the raw tile
+        uint32_t last = 0;
+        if ((tid & 31) == 0) last = (atomicAdd(s_arrive, 1u) % static_cast<uint32_t>(nthr >> 5)) == static_cast<uint32_t>((nthr >> 5) - 1);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {
+          if (i + 1 < ntiles) {
+            if (elect_one()) issue_tile(i + 1);
+          } else if (g + gridDim.x < ngroups) {
+            if (elect_one()) {  // first tile of this CTA's next group
+              const int64_t b0n = (g + gridDim.x) * eb;
+              issue_tile_at(0, b0n, (p.nblocks - b0n) < eb ? static_cast<int>(p.nblocks - b0n) : eb);
+            }
+          }
+          __syncwarp();
+        }
+      };
       for (int c = tid; c < ncol; c += nthr) {
         const int e = c >> 5, x8 = c & 31;
         const uint8_t* rcol = s_raw + e * rawp + x8 * 8;
@@ -260,6 +276,12 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
             lo[t] = v.x; hi[t] = v.y;
             *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
           });
+          if constexpr (AUTO && USE_TMA) {
+            // the raw tile is dead as soon as every lane holds its column in registers: signal it
+            // now so the next TMA batch overlaps the GF arithmetic as well as the hashing
+            __syncwarp();
+            raw_consumed();
+          }
           if constexpr (R > 0) {
             uint32_t olo[R], ohi[R];
             GfStaticApply<typename GF::Mat>::run(lo, olo);
@@ -311,20 +333,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
       }
       if constexpr (AUTO && USE_TMA) {
         __syncwarp();  // (A) this warp's aligned + output rows are complete
-        uint32_t last = 0;
-        if ((tid & 31) == 0) last = (atomicAdd(s_arrive, 1u) % static_cast<uint32_t>(nthr >> 5)) == static_cast<uint32_t>((nthr >> 5) - 1);
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {  // every warp of the CTA has consumed the raw tile: refill it
-          if (i + 1 < ntiles) {
-            if (elect_one()) issue_tile(i + 1);
-          } else if (g + gridDim.x < ngroups) {
-            if (elect_one()) {  // first tile of this CTA's next group
-              const int64_t b0n = (g + gridDim.x) * eb;
-              issue_tile_at(0, b0n, (p.nblocks - b0n) < eb ? static_cast<int>(p.nblocks - b0n) : eb);
-            }
-          }
-          __syncwarp();
-        }
+        if constexpr (!GF::kIsStatic) raw_consumed();
       } else {
         __syncthreads();  // (A) aligned + output tiles complete; raw tile fully consumed
         if (i + 1 < ntiles) {  // refill the raw tile while the hash threads work on the aligned one
