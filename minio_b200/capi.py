@@ -22,7 +22,8 @@ class MecError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libminio_ec.so")
+    # MEC_LIB selects an experimental build variant (tools/build_variants.sh); default is the product library
+    return os.environ.get("MEC_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libminio_ec.so")
 
 
 def lib():

@@ -36,15 +36,18 @@ constexpr int kStaticEb = 4;  // erasure blocks per CTA of the compile-time spec
 
 struct StaticEntry {
   int k, m, sm16;
-  KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb (warp-autonomous when k + m == 16)
-  KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb (warp-autonomous when k + m == 16)
+  KernelFn fast_auto, aligned_auto;  // warp-autonomous pipeline (k + m == 16 only), else nullptr
+  KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb
+  KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb
   KernelFn runtime;   // TMA, any alignment (per-row table), runtime eb
   KernelFn bytewise;  // byte-wise loader, runtime eb
 };
 static const StaticEntry kStaticTable[] = {
 #define X(K, M, A)                                                                                      \
-  {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16)>,                       \
-   fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16)>,                                \
+  {K, M, A, (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16)> : nullptr, \
+   (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16)> : nullptr,          \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, false>,                                        \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, false>,                                        \
    fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0, false>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0, false>},
     MEC_STATIC_CONFIGS(X)
 #undef X
@@ -214,11 +217,11 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   if (se) {
     const int sm16 = static_cast<int>(d.S & 15);
     if (!use_tma) fn = se->bytewise;
-    else if (eb == kStaticEb && sm16 == se->sm16) fn = se->fast;
-    else if (eb == kStaticEb && sm16 == 0) fn = se->aligned;
+    else if (eb == kStaticEb && sm16 == se->sm16) fn = (opt.use_auto && se->fast_auto) ? se->fast_auto : se->fast;
+    else if (eb == kStaticEb && sm16 == 0) fn = (opt.use_auto && se->aligned_auto) ? se->aligned_auto : se->aligned;
     else fn = se->runtime;
   } else {
-    const bool autonomous = (d.k + d.r == 16) && d.digests != nullptr && threads == 32 * eb && !opt.no_auto;
+    const bool autonomous = (d.k + d.r == 16) && d.digests != nullptr && threads == 32 * eb && opt.use_auto;
     fn = !use_tma ? kDynBytewise : (any_misaligned ? kDynRuntime : (autonomous ? kDynAlignedAuto : kDynAligned));
   }
   const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr);

@@ -51,7 +51,7 @@ struct EngineOptions {
   int force_bytewise = 0;  // 1: never use TMA
   int force_dynamic = 0;   // 1: never use the compile-time specialised GF kernels
   int grid_mult = 0;       // CTAs per SM (0 = occupancy)
-  int no_auto = 0;         // 1: never use the warp-autonomous pipeline
+  int use_auto = 0;        // 1: warp-autonomous pipeline (no CTA barriers) when k + r == 16; measured slower, off by default
   int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
 };
 
