@@ -16,7 +16,10 @@
 namespace mec {
 
 #ifndef MEC_XTIME
-#define MEC_XTIME 1
+#define MEC_XTIME 0
+#endif
+#ifndef MEC_HH_VARIANT
+#define MEC_HH_VARIANT 0
 #endif
 
 // ---------------------------------------------------------------- small helpers
@@ -36,27 +39,33 @@ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
 }
 
 // ---------------------------------------------------------------- packed GF(2^8)
-// multiply each of the 4 packed field elements by x (i.e. by 2) modulo x^8+x^4+x^3+x^2+1
-__device__ __forceinline__ uint32_t gf_xtime4(uint32_t a) {
-#if MEC_XTIME == 0
-  // PRMT sign-replicate gives 0xff per byte whose msb is set
-  const uint32_t m = prmt(a, 0u, 0xba98u);
-  return ((a & 0x7f7f7f7fu) << 1) ^ (m & 0x1d1d1d1du);
-#elif MEC_XTIME == 1
-  // one ALU-pipe op (the AND); the msb extraction is an integer subtract and the reduction a
-  // high-half multiply, both on the FMA pipe which this kernel leaves mostly idle
-  const uint32_t t = a & 0x7f7f7f7fu;
-  uint32_t h;
-  asm("sub.u32 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(t));  // == a & 0x80808080 (kept as IADD on purpose)
-  return (t + t) ^ __umulhi(h, 0x1du << 25);
-#elif MEC_XTIME == 2
-  const uint32_t h = a & 0x80808080u;
-  return ((a ^ h) << 1) ^ __umulhi(h, 0x1du << 25);
-#else
-  const uint32_t h = (a >> 7) & 0x01010101u;
-  return ((a & 0x7f7f7f7fu) << 1) ^ (h * 0x1du);
-#endif
+// multiply each of the 4 packed field elements by x (i.e. by 2) modulo x^8+x^4+x^3+x^2+1.
+// Three instruction mixes with different ALU-pipe / FMA-pipe weight (measured in tools/ubench2.cu):
+//   V=0  PRMT sign-replicate + 2 AND (+ shift)      : 3 ALU ops, FMA pipe almost idle
+//   V=1  AND + integer SUB + ADD + high-half multiply: 1 ALU op, ~8 FMA-pipe cycles
+//   V=2  AND + XOR + shift + high-half multiply      : 2 ALU ops, ~6 FMA-pipe cycles
+template <int V>
+__device__ __forceinline__ uint32_t gf_xtime4_v(uint32_t a) {
+  if constexpr (V == 0) {
+    const uint32_t m = prmt(a, 0u, 0xba98u);  // 0xff per byte whose msb is set
+    return ((a & 0x7f7f7f7fu) << 1) ^ (m & 0x1d1d1d1du);
+  } else if constexpr (V == 1) {
+    const uint32_t t = a & 0x7f7f7f7fu;
+    uint32_t h;
+    asm("sub.u32 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(t));  // == a & 0x80808080, kept as an integer op on purpose
+    return (t + t) ^ __umulhi(h, 0x1du << 25);
+  } else {
+    const uint32_t h = a & 0x80808080u;
+    return ((a ^ h) << 1) ^ __umulhi(h, 0x1du << 25);
+  }
 }
+#ifndef MEC_XMIX_NUM
+#define MEC_XMIX_NUM 0   // of every MEC_XMIX_DEN Horner steps, this many use the FMA-heavy variant 1
+#endif
+#ifndef MEC_XMIX_DEN
+#define MEC_XMIX_DEN 4
+#endif
+__device__ __forceinline__ uint32_t gf_xtime4(uint32_t a) { return gf_xtime4_v<MEC_XTIME>(a); }
 
 // Compile-time specialised  out[j] = XOR_t  coef(j,t) (x) in[t]   on packed words.
 // Horner over the bit planes of the coefficients: 7 doublings per OUTPUT word (not per input), and
@@ -80,7 +89,11 @@ struct GfStaticApply {
       uint32_t acc = 0u;
       static_for<8>([&](auto bb_) {
         constexpr int bit = 7 - decltype(bb_)::value;
-        if constexpr (bit != 7) acc = gf_xtime4(acc);
+        if constexpr (bit != 7) {
+          // spread the doublings over both integer pipes: most use the ALU-only form, a fixed fraction the FMA-heavy one
+          constexpr bool fma_heavy = ((bit * R + j) % MEC_XMIX_DEN) < MEC_XMIX_NUM;
+          acc = fma_heavy ? gf_xtime4_v<1>(acc) : gf_xtime4_v<MEC_XTIME>(acc);
+        }
         static_for<G>([&](auto g_) {
           constexpr int g = decltype(g_)::value;
           constexpr int i0 = (MAT::coef(j, 3 * g) >> bit) & 1;
@@ -140,26 +153,60 @@ __device__ __forceinline__ void hh_zipper(uint64_t hi, uint64_t lo, uint64_t& z1
   z1 = pack64(a1l, a1h);
 }
 
-__device__ __forceinline__ void hh_update(HHHalf& s, uint64_t a0, uint64_t a1) {
+// 32 x 32 -> 64 multiply.  MEC_HH_MUL: 0 = mul.wide (IMAD.WIDE), 1 = mul.lo + mul.hi, 2 = mul.wide via PTX with
+// an explicit unpack (the plain C form makes ptxas copy the high word through the ALU before the XOR)
+#ifndef MEC_HH_MUL
+#define MEC_HH_MUL 1
+#endif
+__device__ __forceinline__ uint64_t hh_mul32(uint32_t a, uint32_t b) {
+#if MEC_HH_MUL == 1
+  return pack64(a * b, __umulhi(a, b));
+#elif MEC_HH_MUL == 2
+  uint32_t lo, hi;
+  asm("{\n.reg .b64 t;\nmul.wide.u32 t, %2, %3;\nmov.b64 {%0, %1}, t;\n}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+  return pack64(lo, hi);
+#else
+  return static_cast<uint64_t>(a) * b;
+#endif
+}
+
+// 64-bit add routed through the FMA pipe: x + y as IMAD.WIDE(y.lo, one, x) + (y.hi << 32).  `one` is
+// the value 1 loaded from kernel parameters, so the compiler cannot fold the multiply back into IADD3.
+__device__ __forceinline__ uint64_t add64_fma(uint64_t x, uint64_t y, uint32_t one) {
+  return static_cast<uint64_t>(static_cast<uint32_t>(y)) * one + x + ((y >> 32) << 32);
+}
+
+// HighwayHash Update for the two lanes a thread owns.  MEC_HH_VARIANT moves 64-bit additions from the
+// ALU pipe (IADD3/IADD3.X) to the FMA pipe: 0 = none, 1 = the zipper->v1 add, 2 = also v1 += mul0 + packet.
+__device__ __forceinline__ void hh_update(HHHalf& s, uint64_t a0, uint64_t a1, uint32_t one = 1u) {
   const uint64_t a[2] = {a0, a1};
   uint64_t m1old[2];
 #pragma unroll
   for (int i = 0; i < 2; i++) {
+#if MEC_HH_VARIANT >= 2
+    s.v1[i] = add64_fma(add64_fma(s.v1[i], a[i], one), s.m0[i], one);
+#else
     s.v1[i] += s.m0[i] + a[i];
-    s.m0[i] ^= static_cast<uint64_t>(static_cast<uint32_t>(s.v1[i])) * static_cast<uint32_t>(s.v0[i] >> 32);
+#endif
+    s.m0[i] ^= hh_mul32(static_cast<uint32_t>(s.v1[i]), static_cast<uint32_t>(s.v0[i] >> 32));
     // only the low word of (v0 += mul1) feeds the multiply; the full 64-bit add is merged with the
     // zipper addend below into one 3-input carry chain
     m1old[i] = s.m1[i];
     const uint32_t v0lo = static_cast<uint32_t>(s.v0[i]) + static_cast<uint32_t>(m1old[i]);
-    s.m1[i] ^= static_cast<uint64_t>(v0lo) * static_cast<uint32_t>(s.v1[i] >> 32);
+    s.m1[i] ^= hh_mul32(v0lo, static_cast<uint32_t>(s.v1[i] >> 32));
   }
   uint64_t z1, z0;
   hh_zipper(s.v1[1], s.v1[0], z1, z0);
   s.v0[0] = s.v0[0] + m1old[0] + z0;
   s.v0[1] = s.v0[1] + m1old[1] + z1;
   hh_zipper(s.v0[1], s.v0[0], z1, z0);
+#if MEC_HH_VARIANT >= 1
+  s.v1[0] = add64_fma(s.v1[0], z0, one);
+  s.v1[1] = add64_fma(s.v1[1], z1, one);
+#else
   s.v1[0] += z0;
   s.v1[1] += z1;
+#endif
 }
 
 // byte `pos` (0..31) of the padded remainder packet for a tail of n (1..31) bytes
