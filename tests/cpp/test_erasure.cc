@@ -175,20 +175,28 @@ static void TestErasureEncode() {
 }
 
 static void TestErasureDecode() {
+  // cmd/erasure-decode_test.go:44-83, verbatim minus the algorithm column (the GPU path is HighwayHash256S)
   struct T { int dataBlocks, onDisks, offDisks; int64_t blocksize, data, offset, length; bool shouldFail, shouldFailQuorum; } tests[] = {
-      {2, 4, 0, MiB, MiB, 0, MiB, false, false},           {3, 6, 0, MiB, MiB, 0, MiB, false, false},
-      {4, 8, 1, MiB, MiB, 0, MiB, false, false},           {5, 10, 2, MiB, MiB, 0, MiB, false, false},
-      {6, 12, 3, MiB, MiB, 0, MiB, false, false},          {7, 14, 4, MiB, MiB, 0, MiB, false, false},
-      {8, 16, 7, MiB, MiB, 0, MiB, false, false},          {2, 4, 2, MiB, MiB, 0, MiB, false, true},
-      {4, 8, 4, MiB, MiB, 0, MiB, false, true},            {7, 14, 7, MiB, MiB, 0, MiB, false, true},
-      {8, 16, 8, MiB, MiB, 0, MiB, false, true},           {5, 10, 3, MiB, MiB, 0, MiB, false, false},
-      {3, 6, 1, MiB, MiB, MiB / 2, MiB / 2, false, false}, {2, 4, 0, MiB / 2, MiB, MiB / 2, MiB / 2, false, false},
-      {4, 8, 0, MiB - 1, MiB, MiB - 1, 1, false, false},   {8, 12, 2, MiB, MiB, 2, MiB - 2, false, false},
-      {8, 10, 1, MiB, MiB, 0, MiB, false, false},          {10, 14, 0, MiB, MiB, 17, MiB - 17, false, false},
-      {2, 6, 2, MiB, MiB, MiB / 2, MiB / 2, false, false}, {10, 16, 8, MiB, MiB, 0, MiB, false, true},
-      {2, 4, 0, MiB, MiB, -1, 3, true, false},             {2, 4, 0, MiB, MiB, 1024, -1, true, false},
-      {4, 6, 0, MiB, MiB, 0, MiB, false, false},           {4, 6, 1, MiB, 2 * MiB, 12, MiB + 17, false, false},
-      {4, 6, 3, MiB, 2 * MiB, 1023, 2 * MiB - 1023, false, true}, {8, 12, 4, MiB, 2 * MiB, 11, 2 * MiB - 11, false, false},
+      {2, 4, 0, MiB, MiB, 0, MiB, false, false},            {3, 6, 0, MiB, MiB, 0, MiB, false, false},
+      {4, 8, 0, MiB, MiB, 0, MiB, false, false},            {5, 10, 0, MiB, MiB, 1, MiB - 1, false, false},
+      {6, 12, 0, MiB, MiB, MiB, 0, false, false},           {7, 14, 0, MiB, MiB, 3, 1024, false, false},
+      {8, 16, 0, MiB, MiB, 4, 8 * 1024, false, false},      {7, 14, 7, MiB, MiB, MiB, 1, true, false},
+      {6, 12, 6, MiB, MiB, 0, MiB, false, false},           {5, 10, 5, MiB, MiB, 0, MiB, false, false},
+      {4, 8, 4, MiB, MiB, 0, MiB, false, false},            {3, 6, 3, MiB, MiB, 0, MiB, false, false},
+      {2, 4, 2, MiB, MiB, 0, MiB, false, false},            {2, 4, 1, MiB, MiB, 0, MiB, false, false},
+      {3, 6, 2, MiB, MiB, 0, MiB, false, false},            {4, 8, 3, 2 * MiB, MiB, 0, MiB, false, false},
+      {5, 10, 6, MiB, MiB, 0, MiB, false, true},            {5, 10, 2, MiB, 2 * MiB, MiB, MiB, false, false},
+      {5, 10, 1, MiB, MiB, 0, MiB, false, false},           {6, 12, 3, MiB, MiB, 0, MiB, false, false},
+      {6, 12, 7, MiB, MiB, 0, MiB, false, true},            {8, 16, 8, MiB, MiB, 0, MiB, false, false},
+      {8, 16, 9, MiB, MiB, 0, MiB, false, true},            {8, 16, 7, MiB, MiB, 0, MiB, false, false},
+      {2, 4, 1, MiB, MiB, 0, MiB, false, false},            {2, 4, 0, MiB, MiB, 0, MiB, false, false},
+      {2, 4, 0, MiB, MiB + 1, 0, MiB + 1, false, false},    {2, 4, 0, MiB, 2 * MiB, 12, MiB + 17, false, false},
+      {3, 6, 0, MiB, 2 * MiB, 1023, MiB + 1024, false, false}, {4, 8, 0, MiB, 2 * MiB, 11, MiB + 2 * 1024, false, false},
+      {6, 12, 0, MiB, 2 * MiB, 512, MiB + 8 * 1024, false, false}, {8, 16, 0, MiB, 2 * MiB, MiB, MiB - 1, false, false},
+      {2, 4, 0, MiB, MiB, -1, 3, true, false},              {2, 4, 0, MiB, MiB, 1024, -1, true, false},
+      {4, 6, 0, MiB, MiB, 0, MiB, false, false},            {4, 6, 1, MiB, 2 * MiB, 12, MiB + 17, false, false},
+      {4, 6, 3, MiB, 2 * MiB, 1023, MiB + 1024, false, true}, {8, 12, 4, MiB, 2 * MiB, 11, MiB + 2 * 1024, false, false},
+      // beyond the reference table: the north-star geometry with a range crossing four blocks
       {12, 16, 4, MiB, 5 * MiB + 77, MiB - 3, 3 * MiB + 50, false, false}};
   int idx = 0;
   for (auto& t : tests) {
