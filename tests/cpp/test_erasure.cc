@@ -252,12 +252,16 @@ static void TestErasureDecodeRandomOffsetLength() {
 }
 
 static void TestErasureHeal() {
+  // cmd/erasure-heal_test.go:42-61, verbatim minus the algorithm column
   struct T { int dataBlocks, disks, offDisks, badDisks, badStaleDisks; int64_t blocksize, size; bool shouldFail; } tests[] = {
-      {2, 4, 1, 0, 0, MiB, MiB, false},     {3, 6, 2, 0, 0, MiB, MiB, false},      {4, 8, 2, 1, 0, MiB, MiB, false},
-      {5, 10, 3, 1, 0, MiB, MiB, false},    {6, 12, 2, 3, 0, MiB, MiB, false},     {7, 14, 4, 1, 0, MiB, MiB, false},
-      {8, 16, 6, 1, 0, MiB, MiB, false},    {7, 14, 2, 3, 0, MiB / 2, MiB, false}, {8, 12, 2, 2, 0, MiB / 2, MiB, false},
-      {2, 4, 1, 2, 0, MiB, MiB, true},      {3, 6, 2, 2, 0, MiB, MiB, true},       {2, 4, 0, 3, 3, MiB, MiB, true},
-      {12, 16, 4, 0, 0, MiB, MiB, false},   {7, 10, 1, 0, 0, MiB, 64 * MiB, false}, {4, 8, 4, 1, 0, MiB, MiB, true},
+      {2, 4, 1, 0, 0, MiB, MiB, false},      {3, 6, 2, 0, 0, MiB, MiB, false},      {4, 8, 2, 1, 0, MiB, MiB, false},
+      {5, 10, 3, 1, 0, MiB, MiB, false},     {6, 12, 2, 3, 0, MiB, MiB, false},     {7, 14, 4, 1, 0, MiB, MiB, false},
+      {8, 16, 6, 1, 1, MiB, MiB, false},     {7, 14, 2, 3, 0, MiB / 2, MiB, false}, {6, 12, 1, 0, 1, MiB - 1, MiB, true},
+      {5, 10, 3, 0, 3, MiB / 2, MiB, true},  {4, 8, 1, 1, 0, MiB, MiB, false},      {2, 4, 1, 0, 1, MiB, MiB, true},
+      {6, 12, 8, 3, 0, MiB, MiB, true},      {7, 14, 3, 4, 0, MiB, MiB, false},     {7, 14, 6, 1, 0, MiB, MiB, false},
+      {8, 16, 4, 5, 0, MiB, MiB, true},      {2, 4, 1, 0, 0, MiB, MiB, false},      {12, 16, 2, 1, 0, MiB, MiB, false},
+      {6, 8, 1, 0, 0, MiB, MiB, false},      {2, 4, 1, 0, 0, MiB, 64 * MiB, false},
+      // beyond the reference table: RS(12,4) with four stale drives and a short last block
       {12, 16, 4, 0, 0, MiB, 8 * MiB + 333, false}};
   int idx = 0;
   for (auto& t : tests) {
@@ -285,7 +289,8 @@ static void TestErasureHeal() {
     Err er = s.e->Heal(writers, readers, t.size);
     CHECK((er != Err::nil) == t.shouldFail, "heal %d: err=%d shouldFail=%d", idx, static_cast<int>(er), t.shouldFail);
     if (er == Err::nil)
-      for (int j = 0; j < t.offDisks; j++) CHECK(healed[j]->data == golden[j], "heal %d: healed shard file %d differs", idx, j);
+      for (int j = 0; j < t.offDisks; j++)
+        if (!healed[j]->faulty) CHECK(healed[j]->data == golden[j], "heal %d: healed shard file %d differs", idx, j);
     idx++;
   }
 }
