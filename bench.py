@@ -48,7 +48,7 @@ class ClockSampler:
     def start(self):
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -76,16 +76,29 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(nblocks, reps, threads):
+def cpu_calibrated_run(threads, target_seconds, nblocks=1024):
+    """Bounded CPU sample: calibrate with one pass, then repeat so that ~target_seconds of CPU work are timed."""
+    gib1, sec1, lvl = cpu_reference_run(nblocks, 1, threads)
+    reps = max(1, int(target_seconds / max(sec1, 1e-3)))
+    gib, sec, lvl = cpu_reference_run(nblocks, reps, threads, warm=False)
+    return gib, sec, lvl, nblocks, reps
+
+
+_CPU_BUFS = {}
+
+
+def cpu_reference_run(nblocks, reps, threads, warm=True):
     """The reference's two-pass CPU path (SIMD RS encode, then HighwayHash of every shard) on host cores."""
     import oracle_lib as o
     o.build()
     L = o.lib()
-    rng = np.random.default_rng(0x4D494E494F00 + 2)
-    src = rng.integers(0, 256, nblocks * BS, dtype=np.uint8)
-    parity = np.zeros(nblocks * M * S, dtype=np.uint8)
-    dig = np.zeros(nblocks * (K + M) * 32, dtype=np.uint8)
-    L.orc_encode_hash_blocks_mt(K, M, BS, src.ctypes.data, min(nblocks, 16), parity.ctypes.data, dig.ctypes.data, threads, 1)  # warm
+    if nblocks not in _CPU_BUFS:
+        rng = np.random.default_rng(0x4D494E494F00 + 2)
+        _CPU_BUFS[nblocks] = (rng.integers(0, 256, nblocks * BS, dtype=np.uint8), np.zeros(nblocks * M * S, dtype=np.uint8),
+                              np.zeros(nblocks * (K + M) * 32, dtype=np.uint8))
+    src, parity, dig = _CPU_BUFS[nblocks]
+    if warm:
+        L.orc_encode_hash_blocks_mt(K, M, BS, src.ctypes.data, min(nblocks, 256), parity.ctypes.data, dig.ctypes.data, threads, 1)
     sec = L.orc_encode_hash_blocks_mt(K, M, BS, src.ctypes.data, nblocks, parity.ctypes.data, dig.ctypes.data, threads, reps)
     return nblocks * reps * BS / GiB / sec, sec, L.orc_simd_level().decode()
 
@@ -93,7 +106,7 @@ def cpu_reference_run(nblocks, reps, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--blocks", type=int, default=10240, help="erasure blocks per GPU per step (10240 = 10 GiB)")
@@ -109,14 +122,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        nb = 512  # 512 MiB sample per step
+        nb = 2048  # 2 GiB sample per step (bounded so that K steps end within minutes on a many-core host)
         vals = []
         gib, sec, lvl = cpu_reference_run(nb, 1, threads)  # warm-up
         for _ in range(max(args.warmup - 1, 0)):
-            cpu_reference_run(nb, 1, threads)
-        t0 = time.time()
+            cpu_reference_run(nb, 1, threads, warm=False)
         for _ in range(args.steps):
-            g, s, lvl = cpu_reference_run(nb, 1, threads)
+            g, s, lvl = cpu_reference_run(nb, 1, threads, warm=False)
             vals.append(s)
         ms = 1e3 * sum(vals) / len(vals)
         value = nb * BS / GiB / (sum(vals) / len(vals))
@@ -162,12 +174,12 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()   # samples across warm-up, the timed region and the e2e loop (all GPU-busy)
     for _ in range(max(args.warmup, 3)):
         one_step()
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     l0 = codec.launches
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -177,7 +189,6 @@ def main():
         a.record(stream); one_step(); b.record(stream)
     t_all1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
     launches = codec.launches - l0
     total_ms = t_all0.elapsed_time(t_all1)
     kern_ms = [a.elapsed_time(b) for a, b in evs]
@@ -235,6 +246,7 @@ def main():
             sh = o.encode_data(K, M, h_src[b * BS:(b + 1) * BS].numpy(), fast=True)
             verified &= bool(np.array_equal(h_par.numpy()[(b * M) * S:(b * M + 1) * S], sh[K]))
 
+    clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -256,10 +268,10 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "verified_vs_oracle": verified,
     }
     if not args.no_cpu and world == 1:
-        nb = 256
-        gib, sec, lvl = cpu_reference_run(nb, max(1, int(12 / max(nb * BS / GiB / 8.0, 1e-3)) // 8), threads)
+        gib, sec, lvl, nb, reps = cpu_calibrated_run(threads, 12.0)
         out["cpu_baseline"] = {"value": gib, "unit": "GiB/s", "cores": threads, "kind": "port",
-                               "sample": f"{nb} x 1 MiB blocks, {sec:.1f} s of C oracle ({lvl}) encode then hash, {threads} pthreads"}
+                               "sample": f"{nb} x 1 MiB blocks x {reps} passes = {sec:.1f} s of C oracle ({lvl}): SIMD RS encode, then "
+                                         f"HighwayHash of all 16 shards (two passes, as the reference), {threads} pthreads"}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
