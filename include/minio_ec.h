@@ -95,6 +95,18 @@ int mec_reconstruct_frames(mec_codec* c, const uint8_t* const* frames, int64_t n
                            int64_t last_shard_len, const uint8_t* want, int data_only,
                            uint8_t* const* out, uint8_t* corrupt);
 
+/* Device-resident variant of the fused reconstruct (BASELINE configs 3 and 4): d_frames[i] is a device
+ * pointer to shard file i in frame layout with a 16-byte aligned `frame_pitch` (>= 32 + shard_size;
+ * digest at +0, shard bytes at +32 of every frame), or NULL when the shard is unavailable.  The first k
+ * non-NULL files are read; every shard with want[i] != 0 that was not read is rebuilt into
+ * d_out + (b*r + q)*out_pitch (q = rank of i among the rebuilt shards) and its digest written to
+ * d_digests[(b*(k+r) + k + q)*32]; digests of the k shards read land in d_digests[(b*(k+r) + t)*32] and
+ * d_corrupt[b*k + t] is set when frame t of block b fails its stored digest.  All nblocks are full blocks.
+ * Asynchronous on `cuda_stream`; the fail-over policy stays with the caller (see mec_reconstruct_frames). */
+int mec_reconstruct_device(mec_codec* c, const uint8_t* const* d_frames, int64_t frame_pitch, int64_t nblocks,
+                           const uint8_t* want, int data_only, uint8_t* d_out, int64_t out_pitch,
+                           uint8_t* d_digests, uint8_t* d_corrupt, void* cuda_stream);
+
 /* ---- whole-part drivers ------------------------------------------------------------------- */
 /* Erasure.Encode (cmd/erasure-encode.go:69) with one streaming bitrot writer per shard
  * (cmd/bitrot.go:105, cmd/bitrot-streaming.go:44): files[i] (host, or NULL = offline writer)

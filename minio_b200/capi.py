@@ -54,6 +54,7 @@ def lib():
     L.mec_encode_blocks.argtypes = [vp, vp, i64, vp, vp]
     L.mec_encode_blocks_device.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     L.mec_reconstruct_frames.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp]
+    L.mec_reconstruct_device.argtypes = [vp, vp, i64, i64, vp, i32, vp, i64, vp, vp, vp]
     L.mec_encode.restype = i64
     L.mec_encode.argtypes = [vp, vp, i64, vp, i32]
     L.mec_decode.restype = i64
@@ -146,6 +147,15 @@ class Codec:
         rc = lib().mec_encode_blocks_device(self.h, d_src, length, d_parity, parity_pitch, d_digests, stream)
         if rc:
             raise MecError(rc, "mec_encode_blocks_device")
+
+    def reconstruct_device(self, d_frames, frame_pitch, nblocks, want, data_only, d_out, out_pitch, d_digests, d_corrupt, stream=0):
+        """d_frames: list of k+m device pointers (0/None = unavailable)."""
+        arr = (C.c_void_p * self.n)(*[(p or None) for p in d_frames])
+        want = np.asarray(want, dtype=np.uint8)
+        rc = lib().mec_reconstruct_device(self.h, arr, frame_pitch, nblocks, want.ctypes.data, 1 if data_only else 0,
+                                          d_out, out_pitch, d_digests, d_corrupt, stream)
+        if rc:
+            raise MecError(rc, "mec_reconstruct_device")
 
     # -- whole part
     def encode(self, src, online=None, write_quorum=0):

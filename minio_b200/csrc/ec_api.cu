@@ -424,6 +424,46 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
   return MEC_OK;
 }
 
+extern "C" int mec_reconstruct_device(mec_codec* c, const uint8_t* const* d_frames, int64_t frame_pitch, int64_t nblocks,
+                                      const uint8_t* want, int data_only, uint8_t* d_out, int64_t out_pitch,
+                                      uint8_t* d_digests, uint8_t* d_corrupt, void* stream) {
+  if (!c || !d_frames || !want || nblocks < 0) return MEC_ERR_INVALID_ARGUMENT;
+  int rc = require_streaming(c);
+  if (rc) return rc;
+  if (nblocks == 0) return MEC_OK;
+  const int k = c->k, n = c->n;
+  if (n > kMaxShards || k > kMaxK) return MEC_ERR_UNSUPPORTED;
+  const int64_t S = c->S();
+  if ((frame_pitch & 15) || frame_pitch < 32 + S) return MEC_ERR_INVALID_ARGUMENT;
+  int chosen[kMaxShards], nch = 0;
+  std::vector<uint8_t> present(n, 0);
+  for (int i = 0; i < n && nch < k; i++)
+    if (d_frames[i]) { chosen[nch++] = i; present[i] = 1; }
+  if (nch < k) return MEC_ERR_READ_QUORUM;
+  int targets[kMaxShards], r = 0;
+  for (int i = 0; i < n; i++)
+    if (want[i] && !present[i] && !(data_only && i >= k)) targets[r++] = i;
+  if (r > kMaxR) return MEC_ERR_UNSUPPORTED;
+  std::vector<uint8_t> rows(static_cast<size_t>(std::max(r, 1)) * k);
+  int valid[kMaxShards];
+  if (r > 0 && !rs_decode_rows(k, c->m, present.data(), targets, r, rows.data(), valid)) return MEC_ERR_TOO_FEW_SHARDS;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  FusedDesc d;
+  d.k = k; d.r = r; d.coef = rows.data(); d.static_encode = false; d.contiguous = false;
+  d.key = kMagicKey; d.nblocks = nblocks; d.S = static_cast<int32_t>(S);
+  d.in_block_stride = frame_pitch; d.expect_block_stride = frame_pitch;
+  for (int t = 0; t < k; t++) {
+    const uint8_t* base = d_frames[chosen[t]];
+    d.map_base[t] = base;
+    d.map_len[t] = nblocks * frame_pitch;
+    d.expect_ptr[t] = d_corrupt ? base : nullptr;
+    d.in_ptr[t] = base + 32;
+  }
+  d.out = d_out; d.out_pitch = out_pitch; d.digests = d_digests; d.corrupt = d_corrupt;
+  return c->eng->launch_fused(d, c->opt, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int mec_reconstruct_frames(mec_codec* c, const uint8_t* const* frames, int64_t nblocks, int64_t last_shard_len,
                                       const uint8_t* want, int data_only, uint8_t* const* out, uint8_t* corrupt) {
   if (!c || !frames || !want || !out || nblocks < 0) return MEC_ERR_INVALID_ARGUMENT;

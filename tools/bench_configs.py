@@ -1,0 +1,121 @@
+#!/usr/bin/env python
+"""Device-resident timings of the other BASELINE.json configs (3: reconstruct, 4: heal shape, 5: block-size
+sweep) — parity-checked against the encode outputs; one JSON object per line.  bench.py stays the headline."""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import minio_b200 as mb  # noqa: E402
+
+GiB = float(1 << 30)
+PEAK = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+dev = torch.device("cuda:0")
+
+
+def timeit(fn, steps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+def make_stream(nbytes, seed):
+    g = torch.Generator(device=dev); g.manual_seed(seed)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    step = 1 << 30
+    for o in range(0, nbytes, step):
+        n = min(step, nbytes - o)
+        out[o:o + n] = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+    return out
+
+
+def encode(k, m, bs, nblocks, seed):
+    S = -(-bs // k)
+    pitch = (S + 15) // 16 * 16
+    src = make_stream(nblocks * bs, seed)
+    par = torch.zeros((nblocks * m, pitch), dtype=torch.uint8, device=dev)
+    dig = torch.zeros((nblocks, k + m, 32), dtype=torch.uint8, device=dev)
+    c = mb.Codec(k, m, bs)
+    st = torch.cuda.current_stream().cuda_stream
+    fn = lambda: c.encode_blocks_device(src.data_ptr(), src.numel(), par.data_ptr(), pitch, dig.data_ptr(), st)
+    ms = timeit(fn)
+    return c, src, par, dig, S, pitch, ms
+
+
+def frames_from(k, m, bs, nblocks, src, par, dig, S):
+    fp = (32 + S + 15) // 16 * 16
+    frames = []
+    src2 = src.view(nblocks, bs)
+    par3 = par.view(nblocks, m, -1)
+    for i in range(k + m):
+        f = torch.zeros((nblocks, fp), dtype=torch.uint8, device=dev)
+        f[:, :32] = dig[:, i]
+        if i < k:
+            lo, hi = i * S, min((i + 1) * S, bs)
+            if hi > lo:
+                f[:, 32:32 + hi - lo] = src2[:, lo:hi]
+        else:
+            f[:, 32:32 + S] = par3[:, i - k, :S]
+        frames.append(f)
+    return frames, fp
+
+
+def reconstruct_case(name, k, m, bs, nblocks, erased, seed):
+    c, src, par, dig, S, pitch, enc_ms = encode(k, m, bs, nblocks, seed)
+    frames, fp = frames_from(k, m, bs, nblocks, src, par, dig, S)
+    del src, par
+    n = k + m
+    r = len(erased)
+    want = [1 if i in erased else 0 for i in range(n)]
+    ptrs = [0 if i in erased else frames[i].data_ptr() for i in range(n)]
+    opitch = (S + 15) // 16 * 16
+    out = torch.zeros((nblocks * r, opitch), dtype=torch.uint8, device=dev)
+    odig = torch.zeros((nblocks, k + r, 32), dtype=torch.uint8, device=dev)
+    cor = torch.zeros((nblocks, k), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    fn = lambda: c.reconstruct_device(ptrs, fp, nblocks, want, False, out.data_ptr(), opitch, odig.data_ptr(), cor.data_ptr(), st)
+    ms = timeit(fn)
+    ok = int(cor.sum().item()) == 0
+    o3 = out.view(nblocks, r, opitch)
+    for q, i in enumerate(sorted(erased)):
+        ok &= bool(torch.equal(o3[:, q, :S], frames[i][:, 32:32 + S]))
+        ok &= bool(torch.equal(odig[:, k + q], frames[i][:, :32]))
+    algo = (k + r) * (S + 32)
+    res = {"config": name, "k": k, "m": m, "block_size": bs, "blocks": nblocks, "erased": sorted(erased), "ms": ms,
+           "GiB_per_s_object": nblocks * bs / GiB / (ms / 1e3), "algorithmic_bytes_per_block": algo,
+           "achieved_GBps": algo * nblocks / (ms / 1e3) / 1e9, "frac_of_hbm_peak": algo * nblocks / (ms / 1e3) / 1e9 / PEAK,
+           "bit_exact_vs_encode": ok, "encode_ms_same_shape": enc_ms, "encode_GiB_per_s": nblocks * bs / GiB / (enc_ms / 1e3)}
+    print(json.dumps(res), flush=True)
+    c.close()
+
+
+def sweep(k, m, sizes, total_bytes):
+    for bs in sizes:
+        nblocks = total_bytes // bs
+        c, src, par, dig, S, pitch, ms = encode(k, m, bs, nblocks, 11)
+        algo = bs + m * S + (k + m) * 32
+        print(json.dumps({"config": "5-sweep (HighwayHash256S; SHA256 whole-file bitrot not implemented on the GPU path)", "k": k, "m": m,
+                          "block_size": bs, "blocks": nblocks, "ms": ms, "GiB_per_s_object": nblocks * bs / GiB / (ms / 1e3),
+                          "frac_of_hbm_peak": algo * nblocks / (ms / 1e3) / 1e9 / PEAK}), flush=True)
+        c.close()
+        del src, par, dig
+
+
+if __name__ == "__main__":
+    MiB = 1 << 20
+    reconstruct_case("3a: RS(12,4) reconstruct, data shards {0,1,2,3} erased", 12, 4, MiB, 4096, {0, 1, 2, 3}, 3)
+    reconstruct_case("3b: RS(12,4) reconstruct, shards {1,5,12,15} erased", 12, 4, MiB, 4096, {1, 5, 12, 15}, 3)
+    reconstruct_case("3c: RS(12,4) reconstruct, one data shard erased", 12, 4, MiB, 4096, {3}, 3)
+    reconstruct_case("4: RS(16,4) heal shape, stale {0,7,16,19} (per-GPU slice: 64 objects x 64 MiB)", 16, 4, MiB, 4096, {0, 7, 16, 19}, 4)
+    sweep(8, 8, [64 << 10, 128 << 10, 256 << 10, 512 << 10, MiB, 2 * MiB, 4 * MiB], 1 << 30)
