@@ -126,7 +126,8 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
   const int eb = EB_T > 0 ? EB_T : p.eb;
   const int nstreams = k + r;
   const int tid = threadIdx.x, nthr = blockDim.x;
-  const bool warp0 = __shfl_sync(0xffffffffu, tid >> 5, 0) == 0;  // provably warp-uniform
+  const int warp_id = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
+  const bool warp0 = warp_id == 0;
   const uint32_t rawp = EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch);
   const uint32_t group_bytes = raw_group_bytes(eb, static_cast<int>(rawp));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
@@ -183,18 +184,21 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
     hh_init(hs, p.key, h);
 
     // ---------------- tile loader (raw tile is single-buffered: it is free as soon as GF(i) is done)
-    auto issue_tile_at = [&](int i, int64_t b0, int nb) {  // TMA: one elected lane; byte-wise: all threads
+    // TMA: called by one elected lane per warp; rows are dealt round-robin over `parts` callers so no warp
+    // carries the whole issue cost (part 0 also arms the mbarrier with the total byte count — complete_tx
+    // arriving before expect_tx is legal, the phase cannot complete before the arrival).  Byte-wise: all threads.
+    auto issue_tile_at = [&](int i, int64_t b0, int nb, int part, int parts) {
       if constexpr (USE_TMA) {
         const uint32_t bar = smem_u32(&bars[0]);
         const uint32_t dst0 = smem_u32(s_raw);
         if (p.tma_mode == kLoadTmaBlocks2D) {
-          mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
-          for (int t = 0; t < k; t++)
+          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
+          for (int t = part; t < k; t += parts)
             tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
                         static_cast<int32_t>(b0), bar);
         } else {
-          mbar_expect_tx(bar, static_cast<uint32_t>(k) * nb * kRawRow);
-          for (int t = 0; t < k; t++)
+          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * nb * kRawRow);
+          for (int t = part; t < k; t += parts)
             for (int e = 0; e < nb; e++)
               tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes + e * rawp, &maps.m[t],
                           (p.in_c0[t] + static_cast<int32_t>(b0 + e) * p.in_c0_block_step + i * kTile) >> 2, 0, bar);
@@ -212,7 +216,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
         }
       }
     };
-    auto issue_tile = [&](int i) { issue_tile_at(i, b0, nb); };
+    auto issue_tile = [&](int i) { issue_tile_at(i, b0, nb, 0, 1); };
 
     if constexpr (USE_TMA) {
       // AUTO: later groups are pre-issued by the last arriver of the previous group's final tile
@@ -240,7 +244,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
           } else if (g + gridDim.x < ngroups) {
             if (elect_one()) {  // first tile of this CTA's next group
               const int64_t b0n = (g + gridDim.x) * eb;
-              issue_tile_at(0, b0n, (p.nblocks - b0n) < eb ? static_cast<int>(p.nblocks - b0n) : eb);
+              issue_tile_at(0, b0n, (p.nblocks - b0n) < eb ? static_cast<int>(p.nblocks - b0n) : eb, 0, 1);
             }
           }
           __syncwarp();
@@ -338,10 +342,8 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
         __syncthreads();  // (A) aligned + output tiles complete; raw tile fully consumed
         if (i + 1 < ntiles) {  // refill the raw tile while the hash threads work on the aligned one
           if constexpr (USE_TMA) {
-            if (warp0) {
-              if (elect_one()) issue_tile(i + 1);
-              __syncwarp();
-            }
+            if (elect_one()) issue_tile_at(i + 1, b0, nb, warp_id, nthr >> 5);
+            __syncwarp();
           } else {
             issue_tile(i + 1);  // visible after barrier (B)
           }
