@@ -52,10 +52,15 @@ static const StaticEntry kStaticTable[] = {
     MEC_STATIC_CONFIGS(X)
 #undef X
 };
-static const KernelFn kDynAligned = fused_rs_hh_kernel<GfDynamic, true, 0, 0, false>;
-static const KernelFn kDynAlignedAuto = fused_rs_hh_kernel<GfDynamic, true, 0, 0, true>;
-static const KernelFn kDynRuntime = fused_rs_hh_kernel<GfDynamic, true, kAlignRuntime, 0, false>;
-static const KernelFn kDynBytewise = fused_rs_hh_kernel<GfDynamic, false, 0, 0, false>;
+// runtime-matrix kernels, indexed by row chunk {1, 2, 4}: a single rebuilt shard (the common single-drive
+// failure) costs a quarter of the masked XORs of a four-shard rebuild
+static const KernelFn kDynAligned[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, 0, 0, false>, fused_rs_hh_kernel<GfDynamic<2>, true, 0, 0, false>,
+                                        fused_rs_hh_kernel<GfDynamic<4>, true, 0, 0, false>};
+static const KernelFn kDynRuntime[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, kAlignRuntime, 0, false>,
+                                        fused_rs_hh_kernel<GfDynamic<2>, true, kAlignRuntime, 0, false>,
+                                        fused_rs_hh_kernel<GfDynamic<4>, true, kAlignRuntime, 0, false>};
+static const KernelFn kDynBytewise[3] = {fused_rs_hh_kernel<GfDynamic<1>, false, 0, 0, false>, fused_rs_hh_kernel<GfDynamic<2>, false, 0, 0, false>,
+                                         fused_rs_hh_kernel<GfDynamic<4>, false, 0, 0, false>};
 
 Engine::Engine(int device) : device_(device) {}
 Engine::~Engine() {}
@@ -136,6 +141,9 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   // ---- erasure blocks per CTA and block size
   int eb = opt.eb > 0 ? opt.eb : (128 / (2 * n) > 0 ? 128 / (2 * n) : 1);
   if (opt.eb <= 0 && d.static_encode && d.contiguous) eb = kStaticEb;  // OOB blocks of a partial group read as zeros
+  if (opt.eb <= 0)  // small launches: shrink the CTA until there are at least ~2 CTAs per SM
+    while (eb > 1 && (d.nblocks + eb - 1) / eb < 2ll * num_sms_) eb >>= 1;
+  if (false) {}
   else if (eb > d.nblocks) eb = static_cast<int>(d.nblocks);
   while (eb > 1 && 2 * n * eb > 256) eb--;
   if (eb > 255) eb = 255;
@@ -221,8 +229,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     else if (eb == kStaticEb && sm16 == 0) fn = (opt.use_auto && se->aligned_auto) ? se->aligned_auto : se->aligned;
     else fn = se->runtime;
   } else {
-    const bool autonomous = (d.k + d.r == 16) && d.digests != nullptr && threads == 32 * eb && opt.use_auto;
-    fn = !use_tma ? kDynBytewise : (any_misaligned ? kDynRuntime : (autonomous ? kDynAlignedAuto : kDynAligned));
+    const int rc = d.r <= 1 ? 0 : (d.r == 2 ? 1 : 2);
+    fn = !use_tma ? kDynBytewise[rc] : (any_misaligned ? kDynRuntime[rc] : kDynAligned[rc]);
   }
   const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr);
   if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;

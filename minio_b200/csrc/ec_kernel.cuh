@@ -31,7 +31,7 @@ constexpr int kRowPitch = 288;   // pitch of the aligned data / output tiles (ba
 constexpr int kMaxK = 32;        // inputs supported by the GPU path
 constexpr int kMaxR = 16;        // outputs supported by the GPU path
 constexpr int kMaxMaps = 16;     // tensor maps carried in kernel params
-constexpr int kRChunk = 4;       // rows per pass in the runtime-matrix GF step
+constexpr int kRChunk = 4;       // widest row chunk of the runtime-matrix GF step (mask table padding)
 constexpr int kAlignRuntime = -1;
 
 enum LoaderMode : int { kLoadBytewise = 0, kLoadTmaBlocks2D = 1, kLoadTmaPerInput = 2 };
@@ -68,9 +68,10 @@ struct GfStatic {
   static constexpr int K = K_, R = M_;
   using Mat = EncodeMatrix<K_, M_>;
 };
+template <int RC_>  // rows of the runtime matrix handled per pass over the inputs (1, 2 or 4)
 struct GfDynamic {
   static constexpr bool kIsStatic = false;
-  static constexpr int K = 0, R = 0;
+  static constexpr int K = 0, R = 0, RC = RC_;
 };
 
 __host__ __device__ inline uint32_t raw_group_bytes(int eb, int raw_pitch) { return (static_cast<uint32_t>(eb) * raw_pitch + 127u) & ~127u; }
@@ -294,10 +295,11 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
             for (int j = 0; j < R; j++) store_out(j, make_uint2(olo[j], ohi[j]));
           }
         } else {
-          for (int j0 = 0; j0 < (r > 0 ? r : 1); j0 += kRChunk) {
-            uint32_t pl[kRChunk][8], ph[kRChunk][8];
+          constexpr int RC = GF::RC;
+          for (int j0 = 0; j0 < (r > 0 ? r : 1); j0 += RC) {
+            uint32_t pl[RC][8], ph[RC][8];
 #pragma unroll
-            for (int j = 0; j < kRChunk; j++)
+            for (int j = 0; j < RC; j++)
 #pragma unroll
               for (int b = 0; b < 8; b++) { pl[j][b] = 0u; ph[j][b] = 0u; }
 #pragma unroll 2
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
               if (r == 0) continue;
               const uint4* mk = reinterpret_cast<const uint4*>(s_masks + (t * rpad + j0) * 8);
 #pragma unroll
-              for (int j = 0; j < kRChunk; j++) {
+              for (int j = 0; j < RC; j++) {
                 const uint4 m0 = mk[2 * j], m1 = mk[2 * j + 1];
                 pl[j][0] ^= v.x & m0.x; ph[j][0] ^= v.y & m0.x;
                 pl[j][1] ^= v.x & m0.y; ph[j][1] ^= v.y & m0.y;
@@ -322,7 +324,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
               }
             }
 #pragma unroll
-            for (int j = 0; j < kRChunk; j++) {
+            for (int j = 0; j < RC; j++) {
               if (j0 + j >= r) break;
               uint32_t al = pl[j][7], ah = ph[j][7];
 #pragma unroll
