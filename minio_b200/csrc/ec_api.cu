@@ -99,6 +99,7 @@ extern "C" int mec_codec_new(int k, int m, int64_t block_size, int algo, int dev
   if (const char* e = getenv("MEC_FORCE_DYNAMIC")) c->opt.force_dynamic = atoi(e);
   if (const char* e = getenv("MEC_GRID_MULT")) c->opt.grid_mult = atoi(e);
   if (const char* e = getenv("MEC_USE_AUTO")) c->opt.use_auto = atoi(e);
+  if (const char* e = getenv("MEC_JIT")) c->opt.jit = atoi(e);
   *out = c.release();
   return MEC_OK;
 }
@@ -136,6 +137,7 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else if (!strcmp(name, "force_dynamic")) c->opt.force_dynamic = static_cast<int>(v);
   else if (!strcmp(name, "grid_mult")) c->opt.grid_mult = static_cast<int>(v);
   else if (!strcmp(name, "use_auto")) c->opt.use_auto = static_cast<int>(v);
+  else if (!strcmp(name, "jit")) c->opt.jit = static_cast<int>(v);
   else if (!strcmp(name, "chunk_blocks")) c->opt.chunk_blocks = v;
   else return MEC_ERR_INVALID_ARGUMENT;
   return MEC_OK;

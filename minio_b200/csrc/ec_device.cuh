@@ -8,9 +8,7 @@
 //     10 finalisation rounds exchange lanes (one shuffle pair per round).
 //   * mbarrier / TMA (cp.async.bulk.tensor) wrappers.
 #pragma once
-#include <cuda.h>
-#include <cstdint>
-#include <utility>
+#include "rtc_compat.h"
 #include "gf256.h"
 
 namespace mec {

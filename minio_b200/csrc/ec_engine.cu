@@ -2,8 +2,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <nvrtc.h>
+#include <chrono>
 #include "../../include/minio_ec.h"
 #include "ec_engine.h"
+#include "jit_headers.inc"
 
 namespace mec {
 
@@ -61,6 +65,103 @@ static const KernelFn kDynRuntime[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, k
                                         fused_rs_hh_kernel<GfDynamic<4>, true, kAlignRuntime, 0, false>};
 static const KernelFn kDynBytewise[3] = {fused_rs_hh_kernel<GfDynamic<1>, false, 0, 0, false>, fused_rs_hh_kernel<GfDynamic<2>, false, 0, 0, false>,
                                          fused_rs_hh_kernel<GfDynamic<4>, false, 0, 0, false>};
+
+// ------------------------------------------------------------------------------------------------
+// Run-time specialisation.  Decode matrices depend on which shards survived, so they cannot be
+// compiled ahead of time; the runtime-matrix kernel pays 8·r masked XORs per input word where the
+// compile-time path pays ~9 ops per word for all four outputs.  For large launches the kernel
+// template is therefore instantiated for the concrete matrix with NVRTC (≈0.8 s, cached per
+// (k, r, matrix)) — the GPU analogue of klauspost/reedsolomon caching inverted matrices per pattern.
+#define MEC_STR2(x) #x
+#define MEC_STR(x) MEC_STR2(x)
+struct NvrtcApi {
+  void* h = nullptr;
+  decltype(&nvrtcCreateProgram) create = nullptr;
+  decltype(&nvrtcDestroyProgram) destroy = nullptr;
+  decltype(&nvrtcAddNameExpression) add_name = nullptr;
+  decltype(&nvrtcCompileProgram) compile = nullptr;
+  decltype(&nvrtcGetCUBINSize) cubin_size = nullptr;
+  decltype(&nvrtcGetCUBIN) cubin = nullptr;
+  decltype(&nvrtcGetLoweredName) lowered = nullptr;
+  decltype(&nvrtcGetProgramLogSize) log_size = nullptr;
+  decltype(&nvrtcGetProgramLog) log = nullptr;
+  bool ok = false;
+};
+static NvrtcApi& nvrtc_api() {
+  static NvrtcApi api;
+  static bool tried = false;
+  if (tried) return api;
+  tried = true;
+  for (const char* name : {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"}) {
+    api.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+    if (api.h) break;
+  }
+  if (!api.h) return api;
+#define MEC_SYM(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.h, #sym))
+  MEC_SYM(create, nvrtcCreateProgram); MEC_SYM(destroy, nvrtcDestroyProgram); MEC_SYM(add_name, nvrtcAddNameExpression);
+  MEC_SYM(compile, nvrtcCompileProgram); MEC_SYM(cubin_size, nvrtcGetCUBINSize); MEC_SYM(cubin, nvrtcGetCUBIN);
+  MEC_SYM(lowered, nvrtcGetLoweredName); MEC_SYM(log_size, nvrtcGetProgramLogSize); MEC_SYM(log, nvrtcGetProgramLog);
+#undef MEC_SYM
+  api.ok = api.create && api.destroy && api.add_name && api.compile && api.cubin_size && api.cubin && api.lowered && api.log_size && api.log;
+  return api;
+}
+
+void* Engine::jit_kernel(int k, int r, const uint8_t* coef) {
+  std::string key(reinterpret_cast<const char*>(coef), static_cast<size_t>(k) * r);
+  key = std::to_string(k) + "x" + std::to_string(r) + ":" + key;
+  for (auto& e : jit_cache_)
+    if (e.first == key) return e.second;
+  NvrtcApi& api = nvrtc_api();
+  void* result = nullptr;
+  if (api.ok) {
+    const auto t0 = std::chrono::steady_clock::now();
+    std::string src = "#include \"ec_kernel.cuh\"\nnamespace mec {\nstruct JitMat { static constexpr int K = " + std::to_string(k) +
+                      ", R = " + std::to_string(r) + ";\n  __host__ __device__ static constexpr uint8_t coef(int j, int t) {\n    constexpr uint8_t m[R][K] = {";
+    for (int j = 0; j < r; j++) {
+      src += "{";
+      for (int t = 0; t < k; t++) src += std::to_string(coef[static_cast<size_t>(j) * k + t]) + (t + 1 < k ? "," : "");
+      src += j + 1 < r ? "}," : "}";
+    }
+    src += "};\n    return m[j][t]; } };\nstruct GfJit { static constexpr bool kIsStatic = true; static constexpr int K = JitMat::K, R = JitMat::R; using Mat = JitMat; };\n}\n";
+    const char* names[] = {"rtc_compat.h", "gf256.h", "ec_device.cuh", "ec_kernel.cuh"};
+    const char* bodies[] = {kJitHdr_rtc_compat_h, kJitHdr_gf256_h, kJitHdr_ec_device_cuh, kJitHdr_ec_kernel_cuh};
+    nvrtcProgram prog = nullptr;
+    const char* expr = "mec::fused_rs_hh_kernel<mec::GfJit, true, 0, 0, false>";
+    if (api.create(&prog, src.c_str(), "mec_jit.cu", 4, bodies, names) == NVRTC_SUCCESS) {
+      api.add_name(prog, expr);
+      const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
+                            "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
+                            "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS)};
+      nvrtcResult rc = api.compile(prog, 7, opts);
+      if (rc == NVRTC_SUCCESS) {
+        size_t sz = 0;
+        const char* lname = nullptr;
+        if (api.cubin_size(prog, &sz) == NVRTC_SUCCESS && sz > 0 && api.lowered(prog, expr, &lname) == NVRTC_SUCCESS) {
+          std::vector<char> cubin(sz);
+          api.cubin(prog, cubin.data());
+          cudaLibrary_t lib = nullptr;
+          cudaKernel_t kern = nullptr;
+          if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+              cudaLibraryGetKernel(&kern, lib, lname) == cudaSuccess)
+            result = reinterpret_cast<void*>(kern);
+          else
+            cudaGetLastError();
+        }
+      } else {
+        size_t ls = 0;
+        api.log_size(prog, &ls);
+        std::string log(ls, 0);
+        if (ls) api.log(prog, &log[0]);
+        set_last_error("NVRTC specialisation failed, using the runtime-matrix kernel: " + log.substr(0, 800));
+      }
+      api.destroy(&prog);
+    }
+    jit_compiles_++;
+    jit_seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  }
+  jit_cache_.emplace_back(key, result);  // failures are cached too: never retry, fall back to the generic kernel
+  return result;
+}
 
 Engine::Engine(int device) : device_(device) {}
 Engine::~Engine() {}
@@ -232,19 +333,27 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     const int rc = d.r <= 1 ? 0 : (d.r == 2 ? 1 : 2);
     fn = !use_tma ? kDynBytewise[rc] : (any_misaligned ? kDynRuntime[rc] : kDynAligned[rc]);
   }
-  const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr);
+  const void* kfn = reinterpret_cast<const void*>(fn);
+  bool jitted = false;
+  if (!se && use_tma && !any_misaligned && d.r >= 2) {
+    const int64_t in_bytes = d.nblocks * static_cast<int64_t>(d.S) * d.k;
+    if (opt.jit == 1 || (opt.jit < 0 && in_bytes >= (256ll << 20))) {
+      if (void* jk = jit_kernel(d.k, d.r, d.coef)) { kfn = jk; jitted = true; }
+    }
+  }
+  const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr && !jitted);
   if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;
-  MEC_CUDA_OK(cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   static_cast<int>(smem)));
+  MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;
-  MEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, reinterpret_cast<const void*>(fn), threads, smem));
+  MEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
   if (per_sm < 1) per_sm = 1;
   if (opt.grid_mult > 0 && opt.grid_mult < per_sm) per_sm = opt.grid_mult;
   const int64_t ngroups = (d.nblocks + eb - 1) / eb;
   int64_t grid = static_cast<int64_t>(per_sm) * num_sms_;
   if (grid > ngroups) grid = ngroups;
 
-  fn<<<static_cast<unsigned>(grid), threads, smem, st>>>(p, maps);
+  void* args[] = {&p, &maps};
+  MEC_CUDA_OK(cudaLaunchKernel(kfn, dim3(static_cast<unsigned>(grid)), dim3(static_cast<unsigned>(threads)), args, smem, st));
   MEC_CUDA_OK(cudaGetLastError());
   launches_++;
   return MEC_OK;

@@ -51,6 +51,7 @@ struct EngineOptions {
   int force_bytewise = 0;  // 1: never use TMA
   int force_dynamic = 0;   // 1: never use the compile-time specialised GF kernels
   int grid_mult = 0;       // CTAs per SM (0 = occupancy)
+  int jit = -1;            // decode-matrix kernels specialised at run time with NVRTC: -1 auto (large launches), 0 never, 1 always
   int use_auto = 0;        // 1: warp-autonomous pipeline (no CTA barriers) when k + r == 16; measured slower, off by default
   int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
 };
@@ -63,6 +64,8 @@ class Engine {
   int device() const { return device_; }
   int launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStream_t st);
   int64_t launches() const { return launches_; }
+  int64_t jit_compiles() const { return jit_compiles_; }
+  double jit_seconds() const { return jit_seconds_; }
   int num_sms() const { return num_sms_; }
 
  private:
@@ -70,6 +73,11 @@ class Engine {
   int num_sms_ = 0;
   void* encode_tiled_ = nullptr;  // cuTensorMapEncodeTiled
   int64_t launches_ = 0;
+  // run-time specialised kernels, keyed by (k, r, matrix bytes)
+  void* jit_kernel(int k, int r, const uint8_t* coef);
+  std::vector<std::pair<std::string, void*>> jit_cache_;
+  int64_t jit_compiles_ = 0;
+  double jit_seconds_ = 0;
 };
 
 // grow-only device / pinned buffers

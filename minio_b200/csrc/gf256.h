@@ -4,7 +4,7 @@
 // cmd/erasure-coding.go:63.  Everything is constexpr so the CUDA kernels can be specialised on the
 // matrix at compile time; the same functions run on the host for runtime (decode) matrices.
 #pragma once
-#include <cstdint>
+#include "rtc_compat.h"
 
 namespace mec {
 

@@ -325,3 +325,22 @@ def test_device_resident_large_roundtrip(mb, oracle):
         if stale[i]:
             assert np.array_equal(outs[i], files[i])
     c.close()
+
+
+@pytest.mark.parametrize("k,m,stale", [(12, 4, [0, 1, 2, 3]), (12, 4, [1, 5, 12, 15]), (16, 4, [0, 7, 16, 19]), (8, 8, [0, 1, 2, 3, 8, 9, 10, 11]), (4, 2, [1, 4])])
+def test_heal_with_runtime_specialised_kernels(mb, oracle, k, m, stale):
+    """Decode matrices compiled with NVRTC at run time (option jit=1) must give the same bytes as the generic kernel."""
+    bs, size = MiB, 5 * MiB + 1234
+    data = rand(size, 77)
+    files, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    n = k + m
+    st = [i in stale for i in range(n)]
+    for jit in (1, 0):
+        c = mb.Codec(k, m, bs)
+        c.set_option("jit", jit)
+        outs = c.heal([None if st[i] else files[i] for i in range(n)], st, size)
+        for i in stale:
+            assert np.array_equal(outs[i], files[i]), (jit, i)
+        out, hint = c.decode([None if st[i] else files[i] for i in range(n)], 17, size - 17, size)
+        assert np.array_equal(out, data[17:]) and hint == 0
+        c.close()
