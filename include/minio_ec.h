@@ -126,6 +126,20 @@ int64_t mec_decode(mec_codec* c, const uint8_t* const* files, int64_t offset, in
  * from the readable files (NULL = offline / stale). */
 int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total_length, uint8_t* const* out_files);
 
+/* ---- legacy whole-file bitrot (cmd/bitrot-whole.go, BitrotAlgorithm SHA256 / BLAKE2b512 / HighwayHash256) ----
+ * Erasure.Encode with wholeBitrotWriters (cmd/bitrot-whole.go:35-45): files[i] receives the raw shard file
+ * (shards of all blocks back to back, mec_shard_file_size(len) bytes) and sums + i*64 the digest over the whole
+ * file that bitrotWriterSum (cmd/bitrot.go:148) would return (32 or 64 bytes).  The codec's algorithm must be
+ * one of the whole-file algorithms.  Returns bytes consumed. */
+int64_t mec_encode_whole(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* sums,
+                         int write_quorum);
+/* BitrotAlgorithm.New() hash.Hash one-shot (cmd/bitrot.go:47-64) for a whole-file algorithm: digests of
+ * `count` equal-length messages laid out back to back; digest i at digests + i*mec_digest_size(algo).
+ * Also bitrotVerify's non-streaming branch (cmd/bitrot.go:165-175): hash the file, compare with `want`. */
+int mec_whole_hash(mec_codec* c, int algo, const uint8_t* msgs, int64_t msg_len, int64_t count, uint8_t* digests);
+int mec_bitrot_verify_whole(mec_codec* c, int algo, const uint8_t* file, int64_t file_len, const uint8_t* want);
+int mec_digest_size(int algo);
+
 /* bitrotVerify (cmd/bitrot.go:164) for the streaming algorithm: scans a whole shard file. */
 int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file_len, int64_t part_len);
 

@@ -61,6 +61,11 @@ def lib():
     L.mec_decode.argtypes = [vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
     L.mec_heal.argtypes = [vp, vp, i64, vp]
     L.mec_bitrot_verify.argtypes = [vp, vp, i64, i64]
+    L.mec_encode_whole.restype = i64
+    L.mec_encode_whole.argtypes = [vp, vp, i64, vp, vp, i32]
+    L.mec_whole_hash.argtypes = [vp, i32, vp, i64, i64, vp]
+    L.mec_bitrot_verify_whole.argtypes = [vp, i32, vp, i64, vp]
+    L.mec_digest_size.argtypes = [i32]
     L.mec_rs_encode_shards.argtypes = [vp, vp, i64]
     L.mec_rs_reconstruct_shards.argtypes = [vp, vp, vp, i64, i32]
     L.mec_hh256_batch.argtypes = [vp, vp, i64, i64, vp]
@@ -203,6 +208,32 @@ class Codec:
     def bitrot_verify(self, file, part_len):
         f = _u8(file)
         return lib().mec_bitrot_verify(self.h, f.ctypes.data if f.size else None, f.size, part_len)
+
+    # -- legacy whole-file bitrot
+    def encode_whole(self, src, online=None, write_quorum=0):
+        src = _u8(src)
+        flen = self.shard_file_size(src.size)
+        online = [True] * self.n if online is None else online
+        files = [np.zeros(flen, dtype=np.uint8) if online[i] else None for i in range(self.n)]
+        sums = np.zeros((self.n, 64), dtype=np.uint8)
+        rc = lib().mec_encode_whole(self.h, src.ctypes.data if src.size else None, src.size, _ptrs(files), sums.ctypes.data, write_quorum)
+        if rc < 0:
+            raise MecError(rc, "mec_encode_whole")
+        ds = lib().mec_digest_size(self.algo)
+        return files, [sums[i, :ds].tobytes() for i in range(self.n)]
+
+    def whole_hash(self, algo, msgs, msg_len, count):
+        msgs = _u8(msgs)
+        ds = lib().mec_digest_size(algo)
+        out = np.zeros((count, ds), dtype=np.uint8)
+        rc = lib().mec_whole_hash(self.h, algo, msgs.ctypes.data if msgs.size else None, msg_len, count, out.ctypes.data)
+        if rc:
+            raise MecError(rc, "mec_whole_hash")
+        return out
+
+    def bitrot_verify_whole(self, algo, file, want):
+        f = _u8(file); w = _u8(want)
+        return lib().mec_bitrot_verify_whole(self.h, algo, f.ctypes.data if f.size else None, f.size, w.ctypes.data)
 
     # -- shard shaped
     def rs_encode_shards(self, shards):

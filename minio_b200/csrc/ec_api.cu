@@ -10,6 +10,7 @@
 #include <memory>
 #include "../../include/minio_ec.h"
 #include "ec_engine.h"
+#include "whole_hash.cuh"
 
 using namespace mec;
 
@@ -597,6 +598,120 @@ extern "C" int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file
   for (auto f : flags)
     if (f) return MEC_ERR_FILE_CORRUPT;
   return MEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// legacy whole-file bitrot algorithms
+extern "C" int mec_digest_size(int algo) {
+  switch (algo) {
+    case MEC_SHA256: case MEC_HIGHWAYHASH256: case MEC_HIGHWAYHASH256S: return 32;
+    case MEC_BLAKE2B512: return 64;
+  }
+  return -1;
+}
+
+static int whole_hash_device(mec_codec* c, int algo, const uint8_t* d_data, int64_t pitch, int64_t len, int64_t count,
+                             uint8_t* d_out, cudaStream_t st) {
+  WholeHashParams hp;
+  hp.data = d_data; hp.pitch = pitch; hp.len = len; hp.nstreams = static_cast<int>(count);
+  hp.algo = algo == MEC_HIGHWAYHASH256S ? MEC_HIGHWAYHASH256 : algo;
+  hp.out = d_out;
+  memcpy(hp.key, kMagicKey, 32);
+  const int threads = 64;
+  const int64_t nthreads = hp.algo == MEC_HIGHWAYHASH256 ? 2 * count : count;
+  whole_hash_kernel<<<static_cast<unsigned>((nthreads + threads - 1) / threads), threads, 0, st>>>(hp);
+  MEC_CUDA_OK(cudaGetLastError());
+  (void)c;
+  return MEC_OK;
+}
+
+extern "C" int mec_whole_hash(mec_codec* c, int algo, const uint8_t* msgs, int64_t msg_len, int64_t count, uint8_t* digests) {
+  if (!c || msg_len < 0 || count < 0 || mec_digest_size(algo) < 0) return MEC_ERR_INVALID_ARGUMENT;
+  if (count == 0) return MEC_OK;
+  if (count >= (1ll << 30)) return MEC_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc;
+  if ((rc = ensure_engine(c))) return rc;
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  const int64_t pitch = round_up(msg_len, 16) + 128;  // the kernel reads whole 16-byte vectors
+  if ((rc = s.src.ensure(static_cast<size_t>(count * pitch + 256)))) return rc;
+  if ((rc = s.dig.ensure(static_cast<size_t>(count * 64)))) return rc;
+  if (msg_len > 0)
+    MEC_CUDA_OK(cudaMemcpy2DAsync(s.src.p, static_cast<size_t>(pitch), msgs, static_cast<size_t>(msg_len), static_cast<size_t>(msg_len),
+                                  static_cast<size_t>(count), cudaMemcpyHostToDevice, s.st));
+  if ((rc = whole_hash_device(c, algo, static_cast<const uint8_t*>(s.src.p), pitch, msg_len, count, static_cast<uint8_t*>(s.dig.p), s.st))) return rc;
+  const int ds = mec_digest_size(algo);
+  MEC_CUDA_OK(cudaMemcpy2DAsync(digests, static_cast<size_t>(ds), s.dig.p, 64, static_cast<size_t>(ds), static_cast<size_t>(count),
+                                cudaMemcpyDeviceToHost, s.st));
+  MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+  c->eng->count_launch();
+  return MEC_OK;
+}
+
+extern "C" int mec_bitrot_verify_whole(mec_codec* c, int algo, const uint8_t* file, int64_t file_len, const uint8_t* want) {
+  if (!c || !want || file_len < 0) return MEC_ERR_INVALID_ARGUMENT;
+  uint8_t got[64];
+  int rc = mec_whole_hash(c, algo, file, file_len, 1, got);
+  if (rc) return rc;
+  return memcmp(got, want, static_cast<size_t>(mec_digest_size(algo))) ? MEC_ERR_FILE_CORRUPT : MEC_OK;  // cmd/bitrot.go:171-173
+}
+
+extern "C" int64_t mec_encode_whole(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* sums,
+                                    int write_quorum) {
+  if (!c || len < 0 || !files) return MEC_ERR_INVALID_ARGUMENT;
+  if (c->algo == MEC_HIGHWAYHASH256S) return MEC_ERR_INVALID_ARGUMENT;
+  int online = 0;
+  for (int i = 0; i < c->n; i++) online += files[i] != nullptr;
+  if (online < write_quorum) return MEC_ERR_WRITE_QUORUM;
+  if (c->S() >= (1ll << 31)) return MEC_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc;
+  if ((rc = ensure_engine(c))) return rc;
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  const int k = c->k, m = c->m, n = c->n;
+  const int64_t bs = c->block_size, S = c->S(), pitch = round_up(S, 16);
+  const int64_t nall = ceil_frac(len, bs), flen = mec_shard_file_size(c, len), fpitch = round_up(flen, 16) + 128;
+  Slot& s = c->slots[0];
+  if ((rc = s.src.ensure(static_cast<size_t>(round_up(len, 16) + 256)))) return rc;
+  if ((rc = s.out.ensure(static_cast<size_t>(std::max<int64_t>(nall, 1) * std::max(m, 1) * pitch)))) return rc;
+  if ((rc = s.aux.ensure(static_cast<size_t>(n * fpitch + 256)))) return rc;
+  if ((rc = s.dig.ensure(static_cast<size_t>(n * 64)))) return rc;
+  if (len > 0) {
+    MEC_CUDA_OK(cudaMemcpyAsync(s.src.p, src, static_cast<size_t>(len), cudaMemcpyHostToDevice, s.st));
+    if (m > 0) {  // parity only: the hash is not per block for these algorithms
+      const int64_t nfull = len / bs, tail = len % bs;
+      FusedDesc d;
+      d.k = k; d.r = m; d.coef = c->matrix.data() + static_cast<size_t>(k) * k; d.static_encode = true; d.contiguous = true;
+      d.key = kMagicKey; d.out_pitch = pitch; d.digests = nullptr;
+      if (nfull > 0) {
+        d.nblocks = nfull; d.S = static_cast<int32_t>(S); d.in_base = static_cast<const uint8_t*>(s.src.p);
+        d.in_block_stride = bs; d.in_block_len = bs; d.out = static_cast<uint8_t*>(s.out.p);
+        if ((rc = c->eng->launch_fused(d, c->opt, s.st))) return rc;
+      }
+      if (tail > 0) {
+        d.nblocks = 1; d.S = static_cast<int32_t>(ceil_frac(tail, k)); d.in_base = static_cast<const uint8_t*>(s.src.p) + nfull * bs;
+        d.in_block_stride = round_up(tail, 16); d.in_block_len = tail; d.out = static_cast<uint8_t*>(s.out.p) + nfull * m * pitch;
+        if ((rc = c->eng->launch_fused(d, c->opt, s.st))) return rc;
+      }
+    }
+    GatherParams gp;
+    gp.src = static_cast<const uint8_t*>(s.src.p); gp.parity = static_cast<const uint8_t*>(s.out.p); gp.parity_pitch = pitch;
+    gp.block_size = bs; gp.len = len; gp.k = k; gp.m = m; gp.S = S; gp.files = static_cast<uint8_t*>(s.aux.p);
+    gp.file_pitch = fpitch; gp.file_len = flen;
+    const unsigned gx = static_cast<unsigned>(std::min<int64_t>((flen + 255) / 256, 4096));
+    gather_shard_files_kernel<<<dim3(gx, static_cast<unsigned>(n)), 256, 0, s.st>>>(gp);
+    MEC_CUDA_OK(cudaGetLastError());
+    c->eng->count_launch();
+  }
+  if ((rc = whole_hash_device(c, c->algo, static_cast<const uint8_t*>(s.aux.p), fpitch, flen, n, static_cast<uint8_t*>(s.dig.p), s.st))) return rc;
+  c->eng->count_launch();
+  for (int i = 0; i < n; i++)
+    if (files[i] && flen > 0)
+      MEC_CUDA_OK(cudaMemcpyAsync(files[i], static_cast<uint8_t*>(s.aux.p) + i * fpitch, static_cast<size_t>(flen), cudaMemcpyDeviceToHost, s.st));
+  if (sums) MEC_CUDA_OK(cudaMemcpyAsync(sums, s.dig.p, static_cast<size_t>(n * 64), cudaMemcpyDeviceToHost, s.st));
+  MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+  return len;
 }
 
 // ------------------------------------------------------------------------------------------------

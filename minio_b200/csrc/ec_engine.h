@@ -64,6 +64,7 @@ class Engine {
   int device() const { return device_; }
   int launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStream_t st);
   int64_t launches() const { return launches_; }
+  void count_launch() { launches_++; }
   int64_t jit_compiles() const { return jit_compiles_; }
   double jit_seconds() const { return jit_seconds_; }
   int num_sms() const { return num_sms_; }

@@ -344,3 +344,43 @@ def test_heal_with_runtime_specialised_kernels(mb, oracle, k, m, stale):
         out, hint = c.decode([None if st[i] else files[i] for i in range(n)], 17, size - 17, size)
         assert np.array_equal(out, data[17:]) and hint == 0
         c.close()
+
+
+@pytest.mark.parametrize("algo", [1, 2, 4])  # SHA256, HighwayHash256 (whole-file), BLAKE2b512
+def test_whole_file_bitrot(mb, oracle, algo):
+    """wholeBitrotWriter (cmd/bitrot-whole.go:35-45) + BitrotAlgorithm.New (cmd/bitrot.go:47-64) + bitrotVerify's whole-file
+    branch (:165-175): shard files are raw, one digest over the whole file; also the bitrotSelfTest chain per algorithm."""
+    import hashlib
+    c0 = mb.Codec(2, 2)
+    # hash.Hash shape vs hashlib / oracle, many lengths incl. padding boundaries
+    for n in [0, 1, 31, 32, 55, 56, 63, 64, 65, 111, 112, 127, 128, 129, 255, 1000, 87382, 262144 + 5]:
+        msgs = rand(3 * n, n + algo)
+        got = c0.whole_hash(algo, msgs, n, 3)
+        for i in range(3):
+            assert got[i].tobytes() == oracle.bitrot_hash(algo, msgs[i * n:(i + 1) * n]), (algo, n)
+    if algo == 1:
+        m = rand(5000, 1)
+        assert c0.whole_hash(1, m, 5000, 1)[0].tobytes() == hashlib.sha256(m.tobytes()).digest()
+    # bitrotSelfTest chain (cmd/bitrot.go:224-254)
+    size, bsz = (64, 128) if algo == 4 else ((32, 64) if algo == 1 else (32, 32))
+    msg, s = b"", b""
+    for _ in range(0, size * bsz, size):
+        s = c0.whole_hash(algo, np.frombuffer(msg, dtype=np.uint8), len(msg), 1)[0].tobytes()
+        msg += s
+    assert s.hex() == G.BITROT_SELFTEST[algo]
+    c0.close()
+    # Erasure.Encode with whole-file writers vs the oracle driver
+    for (k, m, bs, length) in [(8, 8, 256 * 1024, 3 * 256 * 1024 + 777), (4, 2, MiB, 2 * MiB), (12, 4, MiB, MiB + 12345), (3, 0, 4096, 10000)]:
+        data = rand(length, 5)
+        want_files, want_sums = oracle.erasure_encode(k, m, bs, algo, data)
+        c = mb.Codec(k, m, bs, algo=algo)
+        files, sums = c.encode_whole(data)
+        for i in range(k + m):
+            assert np.array_equal(files[i], want_files[i]), (algo, k, m, i)
+            assert sums[i] == want_sums[i], (algo, k, m, i)
+            assert c.bitrot_verify_whole(algo, files[i], sums[i]) == 0
+        bad = files[0].copy(); bad[len(bad) // 2] ^= 1
+        assert c.bitrot_verify_whole(algo, bad, sums[0]) == -7
+        with pytest.raises(mb.MecError):
+            c.encode(data)   # the streaming entry point refuses whole-file algorithms
+        c.close()
