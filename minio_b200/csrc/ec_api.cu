@@ -101,6 +101,7 @@ extern "C" int mec_codec_new(int k, int m, int64_t block_size, int algo, int dev
   if (const char* e = getenv("MEC_GRID_MULT")) c->opt.grid_mult = atoi(e);
   if (const char* e = getenv("MEC_USE_AUTO")) c->opt.use_auto = atoi(e);
   if (const char* e = getenv("MEC_JIT")) c->opt.jit = atoi(e);
+  if (const char* e = getenv("MEC_NO_ROWS3D")) c->opt.no_rows3d = atoi(e);
   *out = c.release();
   return MEC_OK;
 }
@@ -139,6 +140,7 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else if (!strcmp(name, "grid_mult")) c->opt.grid_mult = static_cast<int>(v);
   else if (!strcmp(name, "use_auto")) c->opt.use_auto = static_cast<int>(v);
   else if (!strcmp(name, "jit")) c->opt.jit = static_cast<int>(v);
+  else if (!strcmp(name, "no_rows3d")) c->opt.no_rows3d = static_cast<int>(v);
   else if (!strcmp(name, "chunk_blocks")) c->opt.chunk_blocks = v;
   else return MEC_ERR_INVALID_ARGUMENT;
   return MEC_OK;

@@ -40,6 +40,7 @@ constexpr int kStaticEb = 4;  // erasure blocks per CTA of the compile-time spec
 
 struct StaticEntry {
   int k, m, sm16;
+  KernelFn fast3d;    // TMA, S mod 16 == sm16, eb == kStaticEb, one 3-D request per tile
   KernelFn fast_auto, aligned_auto;  // warp-autonomous pipeline (k + m == 16 only), else nullptr
   KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb
   KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb
@@ -48,7 +49,8 @@ struct StaticEntry {
 };
 static const StaticEntry kStaticTable[] = {
 #define X(K, M, A)                                                                                      \
-  {K, M, A, (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16)> : nullptr, \
+  {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, false, true>,                          \
+   (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16)> : nullptr, \
    (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16)> : nullptr,          \
    fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, false>,                                        \
    fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, false>,                                        \
@@ -196,12 +198,12 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_map(void* fn, CUtensorMap* map, const void* base, uint64_t dim0, uint64_t dim1, uint64_t stride1,
-                    uint32_t box0, uint32_t box1) {
-  cuuint64_t dims[2] = {dim0, dim1};
-  cuuint64_t strides[1] = {stride1};
-  cuuint32_t box[2] = {box0, box1};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(base),
+                    uint32_t box0, uint32_t box1, uint64_t dim2 = 0, uint64_t stride2 = 0, uint32_t box2 = 0) {
+  cuuint64_t dims[3] = {dim0, dim1, dim2};
+  cuuint64_t strides[2] = {stride1, stride2};
+  cuuint32_t box[3] = {box0, box1, box2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = reinterpret_cast<EncodeTiledFn>(fn)(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, dim2 ? 3 : 2, const_cast<void*>(base),
                                                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -266,7 +268,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   // fetched from the aligned-down address and the kernel skips in_align[t] bytes.
   const int64_t ntiles = (static_cast<int64_t>(d.S) + kTile - 1) / kTile;
   bool use_tma = !opt.force_bytewise && d.S > 0;
-  bool any_misaligned = false;
+  bool any_misaligned = false, rows3d = false;
   p.in_block_stride = d.in_block_stride;
   p.raw_pitch = kRawRow;
   if (d.contiguous) {
@@ -286,8 +288,27 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     if (use_tma) {
       p.tma_mode = kLoadTmaBlocks2D;
       const uint64_t stride = d.nblocks > 1 ? static_cast<uint64_t>(d.in_block_stride) : static_cast<uint64_t>(d.in_block_len);
+      // 3-D fetch mode (compile-time specialised encode only): rows at the uniform stride S & ~15
+      const int sm16 = static_cast<int>(d.S & 15);
+      const int64_t row_stride = static_cast<int64_t>(d.S) & ~15ll;
+      if (se && !opt.no_rows3d && eb == kStaticEb && sm16 == se->sm16 && d.in_block_len == d.in_block_stride) {
+        const int raw3 = raw_row_3d(d.k, sm16, eb);
+        if (row_stride >= raw3) {
+          CUtensorMap m3;
+          if (make_map(encode_tiled_, &m3, d.in_base, static_cast<uint64_t>(row_stride / 4), static_cast<uint64_t>(d.nblocks), stride,
+                       static_cast<uint32_t>(raw3 / 4), static_cast<uint32_t>(eb), static_cast<uint64_t>(d.k),
+                       static_cast<uint64_t>(row_stride), static_cast<uint32_t>(d.k)) == MEC_OK) {
+            rows3d = true;
+            maps.m[1] = m3;
+            p.tiles_3d = static_cast<int>((row_stride - raw3) / kTile) + 1;
+            p.raw_pitch = raw3;
+            for (int t = 0; t < d.k; t++) p.in_c0[t] = static_cast<int32_t>(t * row_stride);
+          }
+        }
+      }
       int rc = make_map(encode_tiled_, &maps.m[0], d.in_base, static_cast<uint64_t>(d.in_block_len / 4),
-                        static_cast<uint64_t>(d.nblocks), stride, kRawRow / 4, static_cast<uint32_t>(eb));
+                        static_cast<uint64_t>(d.nblocks), stride, static_cast<uint32_t>((rows3d ? p.raw_pitch : kRawRow) / 4),
+                        static_cast<uint32_t>(eb));
       if (rc) return rc;
     }
   } else {
@@ -326,6 +347,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   if (se) {
     const int sm16 = static_cast<int>(d.S & 15);
     if (!use_tma) fn = se->bytewise;
+    else if (rows3d) fn = se->fast3d;
     else if (eb == kStaticEb && sm16 == se->sm16) fn = (opt.use_auto && se->fast_auto) ? se->fast_auto : se->fast;
     else if (eb == kStaticEb && sm16 == 0) fn = (opt.use_auto && se->aligned_auto) ? se->aligned_auto : se->aligned;
     else fn = se->runtime;

@@ -52,6 +52,7 @@ struct EngineOptions {
   int force_dynamic = 0;   // 1: never use the compile-time specialised GF kernels
   int grid_mult = 0;       // CTAs per SM (0 = occupancy)
   int jit = -1;            // decode-matrix kernels specialised at run time with NVRTC: -1 auto (large launches), 0 never, 1 always
+  int no_rows3d = 0;       // 1: never use the one-request-per-tile 3-D TMA fetch
   int use_auto = 0;        // 1: warp-autonomous pipeline (no CTA barriers) when k + r == 16; measured slower, off by default
   int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
 };

@@ -42,6 +42,7 @@ struct alignas(64) TmaMaps {
 
 struct FusedParams {
   int k, r, eb, tma_mode;
+  int tiles_3d;                    // ROWS3D: tiles [0, tiles_3d) of a shard are fetched with one 3-D request
   int raw_pitch;                   // bytes between erasure blocks inside a raw row group (272; 384 when every row is its own TMA box)
   int64_t nblocks;
   int32_t S;                       // shard bytes per erasure block
@@ -84,6 +85,14 @@ __host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, int r
   return b;
 }
 
+// Row width of the raw tile in 3-D fetch mode: every shard row is fetched at the uniform stride S & ~15, so row t
+// carries t * (S mod 16) leading bytes; padded so that eb rows are a multiple of 128 bytes (TMA destinations).
+__host__ __device__ constexpr int raw_row_3d(int k, int sm16, int eb) {
+  int r = (kTile + (k - 1) * sm16 + 15) / 16 * 16;
+  while ((eb * r) % 128) r += 16;
+  return r;
+}
+
 #ifndef MEC_MIN_BLOCKS
 #define MEC_MIN_BLOCKS 3
 #endif
@@ -117,7 +126,10 @@ __device__ __forceinline__ uint2 load_col_rt(const uint8_t* row, uint32_t a) {
 // one erasure block (32 columns, 16 streams x 2 hash threads): the GF -> HH hand-off is then
 // warp-local (__syncwarp) and the only CTA-wide event is "raw tile consumed", tracked by an arrival
 // counter whose last arriver issues the next TMA batch — no __syncthreads in the steady state.
-template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO>
+// ROWS3D: all k rows x eb blocks of a tile arrive with ONE 3-D TMA request (x, block, row) instead of k requests;
+// only the last tiles of a shard, whose box would cross the row stride, fall back to per-row requests (which also
+// provide Split's zero padding through out-of-bounds fill).  Needs a compile-time ALIGN and EB_T.
+template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO, bool ROWS3D = false>
 __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
   extern __shared__ uint8_t smem_raw[];
@@ -129,7 +141,8 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp_id = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const bool warp0 = warp_id == 0;
-  const uint32_t rawp = EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch);
+  constexpr int kRaw3 = ROWS3D ? raw_row_3d(GF::K > 0 ? GF::K : 1, ALIGN > 0 ? ALIGN : 0, EB_T > 0 ? EB_T : 1) : kRawRow;
+  const uint32_t rawp = ROWS3D ? static_cast<uint32_t>(kRaw3) : (EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch));
   const uint32_t group_bytes = raw_group_bytes(eb, static_cast<int>(rawp));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
   uint32_t* s_arrive = reinterpret_cast<uint32_t*>(smem + 64);
@@ -192,7 +205,16 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
       if constexpr (USE_TMA) {
         const uint32_t bar = smem_u32(&bars[0]);
         const uint32_t dst0 = smem_u32(s_raw);
-        if (p.tma_mode == kLoadTmaBlocks2D) {
+        if constexpr (ROWS3D) {
+          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRaw3);
+          if (i < p.tiles_3d) {  // one request for the whole tile
+            if (part == 0) tma_load_3d(dst0, &maps.m[1], i * (kTile / 4), static_cast<int32_t>(b0), 0, bar);
+          } else {               // last tiles of the shard: per-row boxes, zero padding via out-of-bounds fill
+            for (int t = part; t < k; t += parts)
+              tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
+                          static_cast<int32_t>(b0), bar);
+          }
+        } else if (p.tma_mode == kLoadTmaBlocks2D) {
           if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
           for (int t = part; t < k; t += parts)
             tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
@@ -277,7 +299,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
             constexpr int t = decltype(t_)::value;
             uint2 v;
             if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
-            else v = load_col_ct<(t * ALIGN) & 15>(rcol + t * group_bytes);
+            else v = load_col_ct<ROWS3D ? (t * ALIGN) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
             lo[t] = v.x; hi[t] = v.y;
             *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
           });
