@@ -357,7 +357,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   }
   const void* kfn = reinterpret_cast<const void*>(fn);
   bool jitted = false;
-  if (!se && use_tma && !any_misaligned && d.r >= 2) {
+  if (!se && use_tma && !any_misaligned && d.r >= 1) {
     const int64_t in_bytes = d.nblocks * static_cast<int64_t>(d.S) * d.k;
     if (opt.jit == 1 || (opt.jit < 0 && in_bytes >= (256ll << 20))) {
       if (void* jk = jit_kernel(d.k, d.r, d.coef)) { kfn = jk; jitted = true; }
