@@ -108,9 +108,9 @@ static NvrtcApi& nvrtc_api() {
   return api;
 }
 
-void* Engine::jit_kernel(int k, int r, const uint8_t* coef) {
+void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d) {
   std::string key(reinterpret_cast<const char*>(coef), static_cast<size_t>(k) * r);
-  key = std::to_string(k) + "x" + std::to_string(r) + ":" + key;
+  key = std::to_string(k) + "x" + std::to_string(r) + "a" + std::to_string(align) + "e" + std::to_string(eb_t) + (rows3d ? "3" : "2") + ":" + key;
   for (auto& e : jit_cache_)
     if (e.first == key) return e.second;
   NvrtcApi& api = nvrtc_api();
@@ -128,7 +128,9 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef) {
     const char* names[] = {"rtc_compat.h", "gf256.h", "ec_device.cuh", "ec_kernel.cuh"};
     const char* bodies[] = {kJitHdr_rtc_compat_h, kJitHdr_gf256_h, kJitHdr_ec_device_cuh, kJitHdr_ec_kernel_cuh};
     nvrtcProgram prog = nullptr;
-    const char* expr = "mec::fused_rs_hh_kernel<mec::GfJit, true, 0, 0, false>";
+    const std::string expr_s = "mec::fused_rs_hh_kernel<mec::GfJit, true, " + std::to_string(align) + ", " + std::to_string(eb_t) +
+                               ", false, " + (rows3d ? "true" : "false") + ">";
+    const char* expr = expr_s.c_str();
     if (api.create(&prog, src.c_str(), "mec_jit.cu", 4, bodies, names) == NVRTC_SUCCESS) {
       api.add_name(prog, expr);
       const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
@@ -357,10 +359,13 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   }
   const void* kfn = reinterpret_cast<const void*>(fn);
   bool jitted = false;
-  if (!se && use_tma && !any_misaligned && d.r >= 1) {
+  if (!se && use_tma && d.r >= 1 && !opt.force_dynamic) {
     const int64_t in_bytes = d.nblocks * static_cast<int64_t>(d.S) * d.k;
     if (opt.jit == 1 || (opt.jit < 0 && in_bytes >= (256ll << 20))) {
-      if (void* jk = jit_kernel(d.k, d.r, d.coef)) { kfn = jk; jitted = true; }
+      void* jk = nullptr;
+      if (!d.contiguous && !any_misaligned) jk = jit_kernel(d.k, d.r, d.coef, 0, 0, false);            // decode rows, aligned staging
+      else if (d.contiguous && eb == kStaticEb) jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false);  // any (k, m) encode
+      if (jk) { kfn = jk; jitted = true; }
     }
   }
   const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr && !jitted);
