@@ -321,8 +321,8 @@ static int launch_reconstruct(mec_codec* c, const FrameGeom& g, int64_t cur, con
     d.S = static_cast<int32_t>(pass == 0 ? g.S : g.last_len);
     for (int t = 0; t < c->k; t++) {
       const uint8_t* base = static_cast<const uint8_t*>(c->in_files[chosen[t]].p);
-      d.map_base[t] = base;
-      d.map_len[t] = g.dev_bytes();
+      d.map_base[t] = base + first * g.dpitch();
+      d.map_len[t] = g.dev_bytes() - first * g.dpitch();
       d.expect_ptr[t] = base + first * g.dpitch();
       d.in_ptr[t] = base + first * g.dpitch() + 32;
     }
@@ -587,7 +587,7 @@ extern "C" int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file
     const int64_t first = pass == 0 ? 0 : nfull, nb = pass == 0 ? nfull : nblocks - nfull;
     if (nb <= 0) continue;
     d.nblocks = nb; d.S = static_cast<int32_t>(pass == 0 ? S : last_len);
-    d.map_base[0] = base; d.map_len[0] = g.dev_bytes();
+    d.map_base[0] = base + first * P; d.map_len[0] = g.dev_bytes() - first * P;
     d.expect_ptr[0] = base + first * P;
     d.in_ptr[0] = base + first * P + 32;
     d.digests = static_cast<uint8_t*>(s.dig.p) + first * 32;

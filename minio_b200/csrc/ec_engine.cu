@@ -316,14 +316,15 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   } else {
     p.in_limit = d.S;
     p.in_shard_step = 0;
-    if (d.k > kMaxMaps || (d.in_block_stride & 15)) use_tma = false;
+    if (d.k > kMaxMaps || (d.in_block_stride & 15) || (d.nblocks > 1 && d.in_block_stride < d.S)) use_tma = false;
+    // one 2-D map per input stream: dim0 = one block's row (in_block_stride bytes), dim1 = erasure blocks
+    const int64_t row_bytes = d.nblocks > 1 ? d.in_block_stride : ((static_cast<int64_t>(d.S) + 15) / 16 * 16 + 64);
     for (int t = 0; t < d.k; t++) {
       p.in_ptr[t] = d.in_ptr[t];
       if (!use_tma) continue;
-      const int64_t off = d.in_ptr[t] - d.map_base[t];
-      const int64_t max_c0 = off + (d.nblocks - 1) * d.in_block_stride + ntiles * kTile + 64;
-      if ((reinterpret_cast<uintptr_t>(d.map_base[t]) & 15) || off < 0 || max_c0 >= (1ll << 31) ||
-          d.map_len[t] >= (1ll << 33) || d.in_block_stride >= (1ll << 31)) {
+      const int64_t off = d.in_ptr[t] - d.map_base[t];  // offset of the shard inside its block row
+      if ((reinterpret_cast<uintptr_t>(d.map_base[t]) & 15) || off < 0 || off + ntiles * kTile + 64 >= (1ll << 31) ||
+          d.nblocks >= (1ll << 31) || row_bytes >= (1ll << 33) || (d.nblocks > 1 && off + d.S > d.in_block_stride)) {
         use_tma = false;
       } else {
         p.in_c0[t] = static_cast<int32_t>(off & ~15ll);
@@ -333,11 +334,9 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     }
     if (use_tma) {
       p.tma_mode = kLoadTmaPerInput;
-      p.raw_pitch = 384;  // every (input, block) row is its own TMA box: destinations must be 128B-aligned
-      p.in_c0_block_step = static_cast<int32_t>(d.in_block_stride);
       for (int t = 0; t < d.k; t++) {
-        const uint64_t elems = static_cast<uint64_t>((d.map_len[t] + 3) / 4);
-        int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], elems, 1, (elems * 4 + 15) / 16 * 16, kRawRow / 4, 1);
+        int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], static_cast<uint64_t>(row_bytes / 4), static_cast<uint64_t>(d.nblocks),
+                          static_cast<uint64_t>(row_bytes), kRawRow / 4, static_cast<uint32_t>(eb));
         if (rc) return rc;
       }
     }

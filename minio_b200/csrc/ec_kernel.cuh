@@ -219,12 +219,11 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
           for (int t = part; t < k; t += parts)
             tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
                         static_cast<int32_t>(b0), bar);
-        } else {
-          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * nb * kRawRow);
+        } else {  // one map per input stream: rows = erasure blocks of that stream, box {272 B, eb blocks}
+          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
           for (int t = part; t < k; t += parts)
-            for (int e = 0; e < nb; e++)
-              tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes + e * rawp, &maps.m[t],
-                          (p.in_c0[t] + static_cast<int32_t>(b0 + e) * p.in_c0_block_step + i * kTile) >> 2, 0, bar);
+            tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[t], (p.in_c0[t] + i * kTile) >> 2,
+                        static_cast<int32_t>(b0), bar);
         }
       } else {
         const int per_t = eb * kTile;
