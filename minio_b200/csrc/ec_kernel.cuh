@@ -132,6 +132,7 @@ __device__ __forceinline__ uint2 load_col_rt(const uint8_t* row, uint32_t a) {
 template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO, bool ROWS3D = false>
 __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
+  constexpr bool PIPE2 = GF::kIsStatic && USE_TMA && !AUTO && (GF::K + GF::R) >= 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int k = GF::kIsStatic ? GF::K : p.k;
@@ -251,7 +252,90 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
       __syncthreads();
     }
 
-    // ---------------- main tile loop
+    // ---- HH step: packets [8j, 8j+8) of every stream, from the aligned + output tiles
+    auto hh_step = [&](int j) {
+      if (hh_live) {
+        const int q0 = 8 * j;
+        if (q0 + 8 <= npk) {
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const uint4 v = lds128(hh_addr + 32 * q);
+            hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
+          }
+        } else {
+#pragma unroll 1
+          for (int q = 0; q0 + q < npk; q++) {
+            const uint4 v = lds128(hh_addr + 32 * q);
+            hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
+          }
+        }
+        if (j == ntiles - 1 && rem) {
+          const uint8_t* tail = hh_row + ((npk * 32) & (kTile - 1));
+          hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
+        }
+      }
+    };
+
+    // ---------------- software-pipelined tile loop (one column per thread, compile-time matrix):
+    //   wait raw(i) -> columns to registers -> barrier -> TMA(i+1) -> HH(i-1) -> barrier -> aligned tile + GF math
+    // The next raw tile is in flight during a whole hash step AND a whole GF step; still two barriers per tile.
+    if constexpr (PIPE2) {
+      constexpr int K = GF::K, R = GF::R;
+      const int c = tid;
+      const bool colv = c < ncol;
+      const int e = colv ? (c >> 5) : 0, x8 = c & 31;
+      const uint8_t* rcol = s_raw + e * rawp + x8 * 8;
+      uint8_t* crow = s_clean + static_cast<uint32_t>(e * k) * kRowPitch + x8 * 8;
+      uint8_t* prow = s_par + static_cast<uint32_t>(e * r) * kRowPitch + x8 * 8;
+      for (int i = 0; i < ntiles; i++) {
+        mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
+        uint32_t lo[K], hi[K];
+        if (colv) {
+          static_for<K>([&](auto t_) {
+            constexpr int t = decltype(t_)::value;
+            uint2 v;
+            if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
+            else v = load_col_ct<ROWS3D ? (t * ALIGN) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
+            lo[t] = v.x; hi[t] = v.y;
+          });
+        }
+        __syncthreads();  // (A) raw tile consumed; aligned + output tiles of tile i-1 complete
+        if (i + 1 < ntiles) {
+          if (elect_one()) issue_tile_at(i + 1, b0, nb, warp_id, nthr >> 5);
+          __syncwarp();
+        }
+        if (i > 0) hh_step(i - 1);
+        __syncthreads();  // (B) aligned + output tiles may be overwritten
+        if (colv) {
+          const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
+          uint8_t* gout = p.out + (b0 + e) * r * p.out_pitch + xg;
+          const bool full = e < nb && xg + 8 <= S;
+          const bool part = e < nb && xg < S && !full;
+#pragma unroll
+          for (int t = 0; t < K; t++) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = make_uint2(lo[t], hi[t]);
+          if constexpr (R > 0) {
+            uint32_t olo[R], ohi[R];
+            GfStaticApply<typename GF::Mat>::run(lo, olo);
+            GfStaticApply<typename GF::Mat>::run(hi, ohi);
+#pragma unroll
+            for (int j = 0; j < R; j++) {
+              const uint2 o = make_uint2(olo[j], ohi[j]);
+              *reinterpret_cast<uint2*>(prow + j * kRowPitch) = o;
+              uint8_t* gp = gout + j * p.out_pitch;
+              if (full) {
+                *reinterpret_cast<uint2*>(gp) = o;
+              } else if (part) {
+                const uint64_t w = pack64(o.x, o.y);
+                for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
+              }
+            }
+          }
+        }
+      }
+      __syncthreads();  // aligned + output tiles of the last tile complete
+      if (ntiles > 0) hh_step(ntiles - 1);
+    } else {
+    // ---------------- main tile loop (general form)
     for (int i = 0; i < ntiles; i++) {
       if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
 
@@ -373,30 +457,12 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
         }
       }
 
-      // ---- HH step: packets [8i, 8i+8) of every stream
-      if (hh_live) {
-        const int q0 = 8 * i;
-        if (q0 + 8 <= npk) {
-#pragma unroll
-          for (int j = 0; j < 8; j++) {
-            const uint4 v = lds128(hh_addr + 32 * j);
-            hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
-          }
-        } else {
-#pragma unroll 1
-          for (int j = 0; q0 + j < npk; j++) {
-            const uint4 v = lds128(hh_addr + 32 * j);
-            hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
-          }
-        }
-        if (i == ntiles - 1 && rem) {
-          const uint8_t* tail = hh_row + ((npk * 32) & (kTile - 1));
-          hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
-        }
-      }
+      hh_step(i);
       if constexpr (AUTO && USE_TMA) __syncwarp();  // (B) this warp's rows may be overwritten
       else __syncthreads();                          // (B) aligned + output tiles may be overwritten
     }
+
+    }  // !PIPE2
 
     // ---------------- finalisation
     {
