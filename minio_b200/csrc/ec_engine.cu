@@ -135,8 +135,8 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t,
       api.add_name(prog, expr);
       const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
                             "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
-                            "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS)};
-      nvrtcResult rc = api.compile(prog, 7, opts);
+                            "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS), "-DMEC_PIPE2=" MEC_STR(MEC_PIPE2)};
+      nvrtcResult rc = api.compile(prog, 8, opts);
       if (rc == NVRTC_SUCCESS) {
         size_t sz = 0;
         const char* lname = nullptr;

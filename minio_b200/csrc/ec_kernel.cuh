@@ -96,6 +96,9 @@ __host__ __device__ constexpr int raw_row_3d(int k, int sm16, int eb) {
 #ifndef MEC_MIN_BLOCKS
 #define MEC_MIN_BLOCKS 3
 #endif
+#ifndef MEC_PIPE2
+#define MEC_PIPE2 0
+#endif
 
 // one 8-byte column of raw row `row` whose logical byte 0 sits `A` bytes into the row
 template <int A>
@@ -132,7 +135,9 @@ __device__ __forceinline__ uint2 load_col_rt(const uint8_t* row, uint32_t a) {
 template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO, bool ROWS3D = false>
 __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
-  constexpr bool PIPE2 = GF::kIsStatic && USE_TMA && !AUTO && (GF::K + GF::R) >= 16;
+  // MEC_PIPE2: software-pipelined loop (TMA lead of a whole tile).  Measured: removes the mbarrier wait stall but costs
+  // ~3% more instructions; net -1.5% on RS(12,4) at full occupancy, so it is off by default.
+  constexpr bool PIPE2 = MEC_PIPE2 && GF::kIsStatic && USE_TMA && !AUTO && (GF::K + GF::R) >= 16;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   const int k = GF::kIsStatic ? GF::K : p.k;
