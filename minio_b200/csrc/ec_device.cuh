@@ -57,6 +57,20 @@ __device__ __forceinline__ uint32_t gf_xtime4_v(uint32_t a) {
     return ((a ^ h) << 1) ^ __umulhi(h, 0x1du << 25);
   }
 }
+// Division by x: a * x^-1 = (a >> 1) ^ (lsb ? 0x8e : 0), x^-1 = x^7+x^3+x^2+x.  The low bits are peeled off with one
+// AND, removed with an integer subtract and turned into the reduction term with a plain 32-bit multiply (both cheap
+// FMA-pipe ops; 0/1 bytes times 0x8e cannot carry), so a Horner step in x^-1 costs 2 ALU-pipe ops where the
+// doubling above costs 3.  Used with the coefficient decomposition c = sum_b c'_b x^-b (see GfStaticApply).
+__device__ __forceinline__ uint32_t gf_xdiv4(uint32_t a) {
+  const uint32_t l = a & 0x01010101u;
+  uint32_t e;
+  asm("sub.u32 %0, %1, %2;" : "=r"(e) : "r"(a), "r"(l));  // clears the low bit of every byte (kept as an integer op)
+  return (e >> 1) ^ (l * 0x8eu);
+}
+#ifndef MEC_GF_DIV
+#define MEC_GF_DIV 1   // 1: Horner in x^-1 (gf_xdiv4), 0: Horner in x (gf_xtime4)
+#endif
+
 #ifndef MEC_XMIX_NUM
 #define MEC_XMIX_NUM 0   // of every MEC_XMIX_DEN Horner steps, this many use the FMA-heavy variant 1
 #endif
@@ -69,6 +83,16 @@ __device__ __forceinline__ uint32_t gf_xtime4(uint32_t a) { return gf_xtime4_v<M
 // Horner over the bit planes of the coefficients: 7 doublings per OUTPUT word (not per input), and
 // the plane sums are assembled from "four Russians" combinations of input triples, so a
 // (12 -> 4) product costs ~210 integer ops per 4-byte column instead of 48 table multiplies.
+// bit of coefficient c that multiplies Horner plane `plane`: in the x^-1 scheme plane b carries x^-b and
+// c = sum_b c'_b x^-b with c'_b = bit (7-b) of c*x^7; in the x scheme it is simply bit `plane` of c.
+__host__ __device__ constexpr int plane_bit(uint8_t c, int plane) {
+#if MEC_GF_DIV
+  return (gf_mul(c, 0x80) >> (7 - plane)) & 1;
+#else
+  return (c >> plane) & 1;
+#endif
+}
+
 template <class MAT>  // MAT::K, MAT::R, static constexpr uint8_t MAT::coef(j, t)
 struct GfStaticApply {
   static constexpr int K = MAT::K, R = MAT::R, G = (K + 2) / 3;
@@ -86,17 +110,23 @@ struct GfStaticApply {
       constexpr int j = decltype(j_)::value;
       uint32_t acc = 0u;
       static_for<8>([&](auto bb_) {
-        constexpr int bit = 7 - decltype(bb_)::value;
-        if constexpr (bit != 7) {
-          // spread the doublings over both integer pipes: most use the ALU-only form, a fixed fraction the FMA-heavy one
-          constexpr bool fma_heavy = ((bit * R + j) % MEC_XMIX_DEN) < MEC_XMIX_NUM;
+        constexpr int step = decltype(bb_)::value;  // 0 = innermost plane of the Horner scheme
+#if MEC_GF_DIV
+        // c = sum_b c'_b x^-b with c'_b = bit (7-b) of c*x^7; innermost plane is b = 7
+        constexpr int plane = 7 - step;
+        if constexpr (step != 0) acc = gf_xdiv4(acc);
+#else
+        constexpr int plane = 7 - step;  // bit 7 first
+        if constexpr (step != 0) {
+          constexpr bool fma_heavy = ((plane * R + j) % MEC_XMIX_DEN) < MEC_XMIX_NUM;
           acc = fma_heavy ? gf_xtime4_v<1>(acc) : gf_xtime4_v<MEC_XTIME>(acc);
         }
+#endif
         static_for<G>([&](auto g_) {
           constexpr int g = decltype(g_)::value;
-          constexpr int i0 = (MAT::coef(j, 3 * g) >> bit) & 1;
-          constexpr int i1 = (3 * g + 1 < K) ? ((MAT::coef(j, (3 * g + 1 < K) ? 3 * g + 1 : 0) >> bit) & 1) : 0;
-          constexpr int i2 = (3 * g + 2 < K) ? ((MAT::coef(j, (3 * g + 2 < K) ? 3 * g + 2 : 0) >> bit) & 1) : 0;
+          constexpr int i0 = plane_bit(MAT::coef(j, 3 * g), plane);
+          constexpr int i1 = (3 * g + 1 < K) ? plane_bit(MAT::coef(j, (3 * g + 1 < K) ? 3 * g + 1 : 0), plane) : 0;
+          constexpr int i2 = (3 * g + 2 < K) ? plane_bit(MAT::coef(j, (3 * g + 2 < K) ? 3 * g + 2 : 0), plane) : 0;
           constexpr int idx = i0 | (i1 << 1) | (i2 << 2);
           if constexpr (idx != 0) acc ^= cmb[g][idx];
         });

@@ -135,8 +135,9 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t,
       api.add_name(prog, expr);
       const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
                             "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
-                            "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS), "-DMEC_PIPE2=" MEC_STR(MEC_PIPE2)};
-      nvrtcResult rc = api.compile(prog, 8, opts);
+                            "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS), "-DMEC_PIPE2=" MEC_STR(MEC_PIPE2),
+                            "-DMEC_GF_DIV=" MEC_STR(MEC_GF_DIV)};
+      nvrtcResult rc = api.compile(prog, 9, opts);
       if (rc == NVRTC_SUCCESS) {
         size_t sz = 0;
         const char* lname = nullptr;
@@ -263,7 +264,10 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   if (!se) {
     if (d.r > 0 && d.coef == nullptr) return MEC_ERR_INVALID_ARGUMENT;
     for (int j = 0; j < d.r; j++)
-      for (int t = 0; t < d.k; t++) p.coef[j][t] = d.coef[static_cast<size_t>(j) * d.k + t];
+      for (int t = 0; t < d.k; t++) {
+        const uint8_t c = d.coef[static_cast<size_t>(j) * d.k + t];
+        p.coef[j][t] = MEC_GF_DIV ? gf_mul(c, 0x80) : c;  // x^-1 Horner: planes are the bits of c*x^7
+      }
   }
 
   // ---- input addressing + loader choice.  TMA boxes must start on 16-byte boundaries, so each row is
