@@ -85,7 +85,7 @@ __device__ __forceinline__ uint32_t gf_xtime4(uint32_t a) { return gf_xtime4_v<M
 // (12 -> 4) product costs ~210 integer ops per 4-byte column instead of 48 table multiplies.
 // bit of coefficient c that multiplies Horner plane `plane`: in the x^-1 scheme plane b carries x^-b and
 // c = sum_b c'_b x^-b with c'_b = bit (7-b) of c*x^7; in the x scheme it is simply bit `plane` of c.
-constexpr int plane_bit(uint8_t c, int plane) {
+__host__ __device__ constexpr int plane_bit(uint8_t c, int plane) {
 #if MEC_GF_DIV
   return (gf_mul(c, 0x80) >> (7 - plane)) & 1;
 #else
