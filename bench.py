@@ -268,7 +268,7 @@ def main():
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "verified_vs_oracle": verified,
     }
     if not args.no_cpu and world == 1:
-        gib, sec, lvl, nb, reps = cpu_calibrated_run(threads, 12.0)
+        gib, sec, lvl, nb, reps = cpu_calibrated_run(threads, 8.0)  # first pass runs faster than the sustained rate: ~20 s in practice
         out["cpu_baseline"] = {"value": gib, "unit": "GiB/s", "cores": threads, "kind": "port",
                                "sample": f"{nb} x 1 MiB blocks x {reps} passes = {sec:.1f} s of C oracle ({lvl}): SIMD RS encode, then "
                                          f"HighwayHash of all 16 shards (two passes, as the reference), {threads} pthreads"}
