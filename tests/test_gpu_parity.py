@@ -384,3 +384,53 @@ def test_whole_file_bitrot(mb, oracle, algo):
         with pytest.raises(mb.MecError):
             c.encode(data)   # the streaming entry point refuses whole-file algorithms
         c.close()
+
+
+@pytest.mark.parametrize("k,m", [(20, 12), (32, 16), (31, 1), (17, 3)])
+def test_wide_geometries(mb, oracle, k, m):
+    """NewErasure allows k+m <= 256 (cmd/erasure-coding.go:48); the GPU path covers k <= 32, m <= 16."""
+    bs, size = 256 * 1024, 3 * 256 * 1024 + 999
+    data = rand(size, k * 7 + m)
+    want, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    c = mb.Codec(k, m, bs)
+    got = c.encode(data)
+    for i in range(k + m):
+        assert np.array_equal(got[i], want[i]), i
+    stale = [i % 3 == 0 and i < 3 * min(m, 5) for i in range(k + m)]
+    outs = c.heal([None if stale[i] else got[i] for i in range(k + m)], stale, size)
+    for i in range(k + m):
+        if stale[i]:
+            assert np.array_equal(outs[i], want[i]), i
+    c.close()
+
+
+def test_geometry_limits_fail_loudly(mb):
+    c = mb.Codec(33, 4, 1 << 20)          # legal for NewErasure, outside the GPU path
+    with pytest.raises(mb.MecError) as ei:
+        c.encode(rand(1 << 20, 1))
+    assert ei.value.code == -102
+    c.close()
+
+
+def test_decode_random_corruption_matches_oracle(mb, oracle):
+    """Random bit flips in random frames: same bytes out, same readers reported corrupt, same failure when too many."""
+    k, m, bs, size = 6, 3, 65536, 20 * 65536 + 123
+    rng = np.random.default_rng(2024)
+    data = rand(size, 11)
+    files, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    c = mb.Codec(k, m, bs)
+    for trial in range(12):
+        bad = [f.copy() for f in files]
+        nbad = int(rng.integers(0, 5))
+        for i in rng.choice(k + m, nbad, replace=False):
+            bad[i][int(rng.integers(0, bad[i].size))] ^= 1 << int(rng.integers(0, 8))
+        rc, ref, corrupt = oracle.erasure_decode(k, m, bs, oracle.HIGHWAYHASH256S, bad, [1] * (k + m), 0, size, size)
+        if rc == size:
+            out, hint = c.decode(bad, 0, size, size)
+            assert np.array_equal(out, data)
+            assert (hint == -7) == bool(corrupt.any())
+        else:
+            with pytest.raises(mb.MecError) as ei:
+                c.decode(bad, 0, size, size)
+            assert ei.value.code == rc == -10
+    c.close()
