@@ -43,7 +43,7 @@ struct mec_codec {
   EngineOptions opt;
   std::mutex mu;
   Slot slots[kSlots];
-  DevBuf in_files[kMaxK];  // reconstruct: staged survivor frames
+  DevBuf in_files[kMaxShards];  // reconstruct: staged survivor frames, indexed by shard number
   DevBuf flags;
   int64_t S() const { return ceil_frac(block_size, k); }
 };
