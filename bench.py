@@ -253,6 +253,11 @@ def main():
         return
 
     peak, peak_src = read_peaks()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):  # dram__bytes_read + dram__bytes_write of this kernel from the committed ncu capture, scaled per launch
+        tj = json.load(open(tp))
+        traffic = (tj["dram_bytes_read_per_block"] + tj["dram_bytes_write_per_block"]) * nblocks
     kavg_ms = sum(kern_ms) / len(kern_ms)
     achieved = ALGO_BYTES_PER_BLOCK * nblocks / (kavg_ms / 1e3) / 1e9
     out = {
@@ -263,7 +268,7 @@ def main():
                                f"({nbytes / GiB:.2f} GiB stream) per GPU, device-resident",
                    "l2": "inputs (>=10 GiB per step) exceed the 126 MB L2; no explicit flush", "parallelism": f"sets-per-gpu x{world}"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_block": ALGO_BYTES_PER_BLOCK,
+                     "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_block": ALGO_BYTES_PER_BLOCK,
                      "kernel_ms": kavg_ms, "blocks_per_launch": nblocks},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "verified_vs_oracle": verified,
     }
