@@ -142,3 +142,30 @@ def test_simd_variant_matches_scalar(oracle):
     for n in list(range(0, 70)) + [87382, 65536, 1000003]:
         msg = rng.integers(0, 256, n, dtype=np.uint8)
         assert oracle.hh256(msg) == oracle.hh256(msg, fast=True)
+
+
+def test_baseline_config1_cpu_roundtrip(oracle):
+    """BASELINE.json configs[0]: RS(4,2) encode of one 4 MiB object, 1 MiB blocks, HighwayHash256 bitrot, through the
+    C oracle on CPU: frames verify, erase 2 shards -> reconstruct -> bytes equal, heal reproduces the erased files."""
+    k, m, bs, size = 4, 2, 1 << 20, 4 << 20
+    data = np.random.default_rng(0x4D494E494F00 + 1).integers(0, 256, size, dtype=np.uint8)
+    files, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    S = oracle.shard_size(bs, k)
+    assert S == 262144 and all(f.size == 4 * (32 + S) == 1048704 for f in files)
+    for f in files:
+        assert oracle.bitrot_verify(oracle.HIGHWAYHASH256S, f, oracle.shard_file_size(bs, k, size), S) == 0
+    for erased in [(0, 1), (1, 4), (4, 5), (2, 3)]:
+        avail = [0 if i in erased else 1 for i in range(k + m)]
+        rc, out, corrupt = oracle.erasure_decode(k, m, bs, oracle.HIGHWAYHASH256S, files, avail, 0, size, size)
+        assert rc == size and np.array_equal(out, data) and not corrupt.any()
+        rc, healed = oracle.erasure_heal(k, m, bs, oracle.HIGHWAYHASH256S, files, avail, [1 - a for a in avail], size)
+        assert rc == 0
+        for i in erased:
+            assert np.array_equal(healed[i], files[i])
+    # a range read across block boundaries and one flipped bit (detected, still decodable)
+    rc, out, _ = oracle.erasure_decode(k, m, bs, oracle.HIGHWAYHASH256S, files, [1] * 6, bs - 5, 2 * bs + 10, size)
+    assert rc == 2 * bs + 10 and np.array_equal(out, data[bs - 5:3 * bs + 5])
+    bad = [f.copy() for f in files]
+    bad[2][100000] ^= 0x10
+    rc, out, corrupt = oracle.erasure_decode(k, m, bs, oracle.HIGHWAYHASH256S, bad, [1] * 6, 0, size, size)
+    assert rc == size and np.array_equal(out, data) and corrupt.tolist() == [0, 0, 1, 0, 0, 0]
