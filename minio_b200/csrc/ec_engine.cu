@@ -108,10 +108,17 @@ static NvrtcApi& nvrtc_api() {
   return api;
 }
 
+// The cache is process-wide (per device): MinIO builds one Erasure per request (cmd/erasure-object.go:1371), so a
+// per-codec cache would recompile the same erasure pattern for every object of a heal sweep.
+static std::mutex g_jit_mu;
+static std::vector<std::pair<std::string, void*>> g_jit_cache;
+
 void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d) {
   std::string key(reinterpret_cast<const char*>(coef), static_cast<size_t>(k) * r);
-  key = std::to_string(k) + "x" + std::to_string(r) + "a" + std::to_string(align) + "e" + std::to_string(eb_t) + (rows3d ? "3" : "2") + ":" + key;
-  for (auto& e : jit_cache_)
+  key = "d" + std::to_string(device_) + ":" + std::to_string(k) + "x" + std::to_string(r) + "a" + std::to_string(align) + "e" +
+        std::to_string(eb_t) + (rows3d ? "3" : "2") + ":" + key;
+  std::lock_guard<std::mutex> lk(g_jit_mu);
+  for (auto& e : g_jit_cache)
     if (e.first == key) return e.second;
   NvrtcApi& api = nvrtc_api();
   void* result = nullptr;
@@ -164,7 +171,7 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t,
     jit_compiles_++;
     jit_seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   }
-  jit_cache_.emplace_back(key, result);  // failures are cached too: never retry, fall back to the generic kernel
+  g_jit_cache.emplace_back(key, result);  // failures are cached too: never retry, fall back to the generic kernel
   return result;
 }
 
