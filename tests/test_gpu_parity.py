@@ -434,3 +434,35 @@ def test_decode_random_corruption_matches_oracle(mb, oracle):
                 c.decode(bad, 0, size, size)
             assert ei.value.code == rc == -10
     c.close()
+
+
+def test_concurrent_callers(mb, oracle):
+    """Thousands of request goroutines share codecs in MinIO (SURVEY §8b 'Threading'): one codec used from several
+    threads, and several codecs on one device at once, must stay bit-exact."""
+    import threading
+    k, m, bs = 12, 4, MiB
+    datas = [rand(3 * MiB + 1000 * i + 7, 100 + i) for i in range(6)]
+    wants = [oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, d)[0] for d in datas]
+    shared = mb.Codec(k, m, bs)
+    errors = []
+
+    def worker(i, codec):
+        try:
+            for _ in range(3):
+                got = codec.encode(datas[i])
+                assert all(np.array_equal(a, b) for a, b in zip(got, wants[i]))
+                out, hint = codec.decode([None, None] + got[2:], 5, datas[i].size - 5, datas[i].size)
+                assert np.array_equal(out, datas[i][5:]) and hint == 0
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    own = [mb.Codec(k, m, bs) for _ in range(3)]
+    threads = [threading.Thread(target=worker, args=(i, shared if i < 3 else own[i - 3])) for i in range(6)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    shared.close()
+    for c in own:
+        c.close()
