@@ -71,6 +71,19 @@ __device__ __forceinline__ uint32_t gf_xdiv4(uint32_t a) {
 #define MEC_GF_DIV 0   // 1: Horner in x^-1 (gf_xdiv4), 0: Horner in x (gf_xtime4).  Measured: the x^-1 form saves an ALU op per step but c*x^7 is denser than the (sparse) RS coefficients, so it loses overall.
 #endif
 
+// One Horner step  acc*x ^ x_terms  in 3 ALU-pipe ops + 1 FMA-pipe op: the byte-msb mask comes from PRMT, the
+// doubling is a plain 32-bit add whose cross-byte carry-in bit is masked INSIDE the final LOP3
+// ((a+a) & 0xfefefefe == (a & 0x7f7f7f7f) << 1), and the reduction mask is folded into the LOP3 that adds the terms.
+__device__ __forceinline__ uint32_t gf_xtime_add4(uint32_t a, uint32_t x_terms) {
+  const uint32_t m = prmt(a, 0u, 0xba98u);  // 0xff per byte whose msb is set
+  const uint32_t a2 = a + a;
+  const uint32_t y = (m & 0x1d1d1d1du) ^ x_terms;
+  return (a2 & 0xfefefefeu) ^ y;
+}
+#ifndef MEC_FUSED_STEP
+#define MEC_FUSED_STEP 1   // 1: gf_xtime_add4 (shipped), 0: separate doubling + XOR accumulation
+#endif
+
 #ifndef MEC_XMIX_NUM
 #define MEC_XMIX_NUM 0   // of every MEC_XMIX_DEN Horner steps, this many use the FMA-heavy variant 1
 #endif
@@ -127,6 +140,16 @@ struct GfStaticApply {
       static_for<8>([&](auto bb_) {
         constexpr int step = decltype(bb_)::value;  // 0 = innermost plane of the Horner scheme
         constexpr int plane = 7 - step;
+#if MEC_FUSED_STEP && !MEC_GF_DIV
+        uint32_t terms = 0u;
+        static_for<G>([&](auto g_) {
+          constexpr int g = decltype(g_)::value;
+          constexpr int idx = combo_index(j, g, plane);
+          if constexpr (idx != 0) terms ^= cmb[g][idx];
+        });
+        if constexpr (step != 0) acc = gf_xtime_add4(acc, terms);
+        else acc = terms;
+#else
 #if MEC_GF_DIV
         if constexpr (step != 0) acc = gf_xdiv4(acc);
 #else
@@ -140,6 +163,7 @@ struct GfStaticApply {
           constexpr int idx = combo_index(j, g, plane);
           if constexpr (idx != 0) acc ^= cmb[g][idx];
         });
+#endif
       });
       out[j] = acc;
     });

@@ -143,8 +143,9 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t,
       const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
                             "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
                             "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS), "-DMEC_PIPE2=" MEC_STR(MEC_PIPE2),
-                            "-DMEC_GF_DIV=" MEC_STR(MEC_GF_DIV)};
-      nvrtcResult rc = api.compile(prog, 9, opts);
+                            "-DMEC_GF_DIV=" MEC_STR(MEC_GF_DIV), "-DMEC_GF_GROUP=" MEC_STR(MEC_GF_GROUP),
+                            "-DMEC_FUSED_STEP=" MEC_STR(MEC_FUSED_STEP)};
+      nvrtcResult rc = api.compile(prog, 11, opts);
       if (rc == NVRTC_SUCCESS) {
         size_t sz = 0;
         const char* lname = nullptr;

@@ -446,6 +446,9 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
 #if MEC_GF_DIV
                 al = gf_xdiv4(al) ^ pl[j][b];
                 ah = gf_xdiv4(ah) ^ ph[j][b];
+#elif MEC_FUSED_STEP
+                al = gf_xtime_add4(al, pl[j][b]);
+                ah = gf_xtime_add4(ah, ph[j][b]);
 #else
                 al = gf_xtime4(al) ^ pl[j][b];
                 ah = gf_xtime4(ah) ^ ph[j][b];
