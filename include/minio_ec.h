@@ -76,7 +76,7 @@ int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* pa
 /* Same, device-resident: d_src/d_parity/d_digests are device pointers on the codec's device,
  * d_src 16-byte aligned, parity row pitch `parity_pitch` (multiple of 16, >= shard_size):
  * parity shard (b, j) at d_parity + (b*m + j)*parity_pitch.  Asynchronous on `cuda_stream`
- * (a cudaStream_t, may be NULL). */
+ * (a cudaStream_t, may be NULL).  d_digests == NULL computes parity only (whole-file bitrot algorithms). */
 int mec_encode_blocks_device(mec_codec* c, const uint8_t* d_src, int64_t len, uint8_t* d_parity,
                              int64_t parity_pitch, uint8_t* d_digests, void* cuda_stream);
 
@@ -138,6 +138,10 @@ int64_t mec_encode_whole(mec_codec* c, const uint8_t* src, int64_t len, uint8_t*
  * Also bitrotVerify's non-streaming branch (cmd/bitrot.go:165-175): hash the file, compare with `want`. */
 int mec_whole_hash(mec_codec* c, int algo, const uint8_t* msgs, int64_t msg_len, int64_t count, uint8_t* digests);
 int mec_bitrot_verify_whole(mec_codec* c, int algo, const uint8_t* file, int64_t file_len, const uint8_t* want);
+/* Device-resident mec_whole_hash: message i at d_msgs + i*pitch (pitch a multiple of 16, >= msg_len, with 128 readable
+ * bytes after the last message), digest i at d_digests + i*64.  Asynchronous on `cuda_stream`. */
+int mec_whole_hash_device(mec_codec* c, int algo, const uint8_t* d_msgs, int64_t pitch, int64_t msg_len, int64_t count,
+                          uint8_t* d_digests, void* cuda_stream);
 int mec_digest_size(int algo);
 
 /* bitrotVerify (cmd/bitrot.go:164) for the streaming algorithm: scans a whole shard file. */

@@ -66,6 +66,7 @@ def lib():
     L.mec_whole_hash.argtypes = [vp, i32, vp, i64, i64, vp]
     L.mec_bitrot_verify_whole.argtypes = [vp, i32, vp, i64, vp]
     L.mec_digest_size.argtypes = [i32]
+    L.mec_whole_hash_device.argtypes = [vp, i32, vp, i64, i64, i64, vp, vp]
     L.mec_rs_encode_shards.argtypes = [vp, vp, i64]
     L.mec_rs_reconstruct_shards.argtypes = [vp, vp, vp, i64, i32]
     L.mec_hh256_batch.argtypes = [vp, vp, i64, i64, vp]
@@ -230,6 +231,11 @@ class Codec:
         if rc:
             raise MecError(rc, "mec_whole_hash")
         return out
+
+    def whole_hash_device(self, algo, d_msgs, pitch, msg_len, count, d_digests, stream=0):
+        rc = lib().mec_whole_hash_device(self.h, algo, d_msgs, pitch, msg_len, count, d_digests, stream)
+        if rc:
+            raise MecError(rc, "mec_whole_hash_device")
 
     def bitrot_verify_whole(self, algo, file, want):
         f = _u8(file); w = _u8(want)

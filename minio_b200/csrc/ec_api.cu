@@ -191,8 +191,13 @@ static int encode_device_locked(mec_codec* c, const uint8_t* d_src, int64_t len,
 extern "C" int mec_encode_blocks_device(mec_codec* c, const uint8_t* d_src, int64_t len, uint8_t* d_parity,
                                         int64_t parity_pitch, uint8_t* d_digests, void* stream) {
   if (!c || len < 0) return MEC_ERR_INVALID_ARGUMENT;
-  int rc = require_streaming(c);
-  if (rc) return rc;
+  int rc;
+  if (d_digests == nullptr) {  // parity only (whole-file bitrot algorithms hash separately, mec_whole_hash_device)
+    std::lock_guard<std::mutex> lk0(c->mu);
+    if ((rc = ensure_engine(c))) return rc;
+  } else if ((rc = require_streaming(c))) {
+    return rc;
+  }
   if (len == 0) return MEC_OK;
   if (c->S() >= (1ll << 31)) return MEC_ERR_UNSUPPORTED;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -647,6 +652,20 @@ extern "C" int mec_whole_hash(mec_codec* c, int algo, const uint8_t* msgs, int64
   MEC_CUDA_OK(cudaMemcpy2DAsync(digests, static_cast<size_t>(ds), s.dig.p, 64, static_cast<size_t>(ds), static_cast<size_t>(count),
                                 cudaMemcpyDeviceToHost, s.st));
   MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+  c->eng->count_launch();
+  return MEC_OK;
+}
+
+extern "C" int mec_whole_hash_device(mec_codec* c, int algo, const uint8_t* d_msgs, int64_t pitch, int64_t msg_len, int64_t count,
+                                     uint8_t* d_digests, void* stream) {
+  if (!c || msg_len < 0 || count < 0 || mec_digest_size(algo) < 0 || (pitch & 15) || pitch < msg_len) return MEC_ERR_INVALID_ARGUMENT;
+  if (count == 0) return MEC_OK;
+  if (count >= (1ll << 30)) return MEC_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc;
+  if ((rc = ensure_engine(c))) return rc;
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  if ((rc = whole_hash_device(c, algo, d_msgs, pitch, msg_len, count, d_digests, static_cast<cudaStream_t>(stream)))) return rc;
   c->eng->count_launch();
   return MEC_OK;
 }

@@ -158,6 +158,36 @@ def sweep(k, m, sizes, total_bytes):
         del src, par, dig
 
 
+def sha256_sweep(k, m, sizes, total_bytes):
+    """BASELINE config 5: RS(8,8) with SHA256 whole-file bitrot, one-block objects (one digest per shard file), block-size sweep.
+    Parity from the fused kernel without hashing, then one SHA-256 stream per shard (`whole_hash.cuh`); checked with hashlib."""
+    import hashlib
+    for bs in sizes:
+        nblocks = total_bytes // bs
+        S = bs // k
+        pitch = (S + 15) // 16 * 16
+        src = torch.cat([make_stream(nblocks * bs, 5), torch.zeros(256, dtype=torch.uint8, device=dev)])
+        par = torch.zeros((nblocks * m + 1, pitch), dtype=torch.uint8, device=dev)
+        dig = torch.zeros((nblocks * (k + m), 64), dtype=torch.uint8, device=dev)
+        c = mb.Codec(k, m, bs, algo=mb.SHA256)
+        st = torch.cuda.current_stream().cuda_stream
+
+        def fn():
+            c.encode_blocks_device(src.data_ptr(), nblocks * bs, par.data_ptr(), pitch, 0, st)
+            c.whole_hash_device(mb.SHA256, src.data_ptr(), S, S, nblocks * k, dig.data_ptr(), st)               # data shard (b, t) = stream b*k+t
+            c.whole_hash_device(mb.SHA256, par.data_ptr(), pitch, S, nblocks * m, dig.data_ptr() + nblocks * k * 64, st)
+        ms = timeit(fn, steps=5, warm=2)
+        h_src = src[:bs].cpu().numpy().tobytes(); h_par = par[:m, :S].cpu().numpy(); h_dig = dig.cpu().numpy()
+        ok = all(hashlib.sha256(h_src[t * S:(t + 1) * S]).digest() == h_dig[t, :32].tobytes() for t in range(k))
+        ok &= all(hashlib.sha256(h_par[j].tobytes()).digest() == h_dig[nblocks * k + j, :32].tobytes() for j in range(m))
+        algo = bs + m * S
+        print(json.dumps({"config": "5: RS(%d,%d) + SHA256 whole-file bitrot, one-block objects" % (k, m), "k": k, "m": m, "block_size": bs,
+                          "blocks": nblocks, "ms": ms, "GiB_per_s_object": nblocks * bs / GiB / (ms / 1e3),
+                          "frac_of_hbm_peak": algo * nblocks / (ms / 1e3) / 1e9 / PEAK, "bit_exact_vs_encode": bool(ok)}), flush=True)
+        c.close()
+        del src, par, dig
+
+
 if __name__ == "__main__":
     MiB = 1 << 20
     reconstruct_case("3a: RS(12,4) reconstruct, data shards {0,1,2,3} erased", 12, 4, MiB, 4096, {0, 1, 2, 3}, 3)
@@ -167,4 +197,5 @@ if __name__ == "__main__":
     verify_case(12, 4, MiB, 4096, 9)
     jit_encode_case(10, 4, MiB, 4096)
     jit_encode_case(7, 5, MiB, 2048)
+    sha256_sweep(8, 8, [64 << 10, 256 << 10, MiB, 4 * MiB], 1 << 30)
     sweep(8, 8, [64 << 10, 128 << 10, 256 << 10, 512 << 10, MiB, 2 * MiB, 4 * MiB], 1 << 30)
