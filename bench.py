@@ -199,6 +199,29 @@ def main():
     ms_per_step = total_ms / args.steps
     value = world * nbytes / GiB / (ms_per_step / 1e3)
 
+    # ---- input scatter over NVLink: rank 0 owns a single-source stream and hands every rank its slice
+    # with NCCL; timed separately from the kernel metric (the data path itself has no collective)
+    scatter = None
+    if world > 1:
+        per = 1 << 30
+        recv = torch.empty(per, dtype=torch.uint8, device=dev)
+        chunks = [src[(i % 8) * per:(i % 8 + 1) * per] for i in range(world)] if rank == 0 else None
+        for _ in range(2):
+            dist.scatter(recv, chunks, src=0)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(3):
+            dist.scatter(recv, chunks, src=0)
+        s1.record(stream)
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1) / 3], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sms = float(t.item())
+        scatter = {"bytes_per_rank": per, "ms": sms, "egress_GBps_rank0": (world - 1) * per / (sms / 1e3) / 1e9,
+                   "note": "NCCL scatter from rank 0, timed apart from the encode kernel"}
+        del recv
+
     # ---- spot verification against the oracle (outside the timed region)
     verified = None
     if rank == 0:
@@ -272,6 +295,8 @@ def main():
                      "kernel_ms": kavg_ms, "blocks_per_launch": nblocks},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "verified_vs_oracle": verified,
     }
+    if scatter:
+        out["scatter"] = scatter
     if not args.no_cpu and world == 1:
         gib, sec, lvl, nb, reps = cpu_calibrated_run(threads, 8.0)  # first pass runs faster than the sustained rate: ~20 s in practice
         out["cpu_baseline"] = {"value": gib, "unit": "GiB/s", "cores": threads, "kind": "port",
