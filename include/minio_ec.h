@@ -122,6 +122,12 @@ int64_t mec_encode(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const
 int64_t mec_decode(mec_codec* c, const uint8_t* const* files, int64_t offset, int64_t length,
                    int64_t total_length, uint8_t* dst, int* heal_hint);
 
+/* Same with parallelReader.preferReaders (cmd/erasure-decode.go:92-123; `prefer` as passed by
+ * cmd/erasure-object.go:387 for local drives): readers with prefer[i] != 0 are tried before the others, each
+ * class in index order.  prefer == NULL is mec_decode. */
+int64_t mec_decode_prefer(mec_codec* c, const uint8_t* const* files, const uint8_t* prefer, int64_t offset,
+                          int64_t length, int64_t total_length, uint8_t* dst, int* heal_hint);
+
 /* Erasure.Heal (cmd/erasure-decode.go:317): rebuilds every shard file with out_files[i] != NULL
  * from the readable files (NULL = offline / stale). */
 int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total_length, uint8_t* const* out_files);
@@ -163,6 +169,10 @@ int mec_selftest(int device);
 
 /* tuning knobs for benchmarks/tests (erasure blocks per CTA, loader, GF specialisation) */
 int mec_set_option(mec_codec* c, const char* name, int64_t value);
+/* Boundary counters (SURVEY §5 metrics row): name is one of "launches", "blocks_encoded", "blocks_read",
+ * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms".  -1 for unknown names.
+ * Every ABI call is also wrapped in an NVTX range (visible in Nsight Systems) — the tracing hook of SURVEY §5. */
+int64_t mec_get_stat(const mec_codec* c, const char* name);
 /* number of kernels launched by this codec so far (bench.py's gpu_launches) */
 int64_t mec_launch_count(const mec_codec* c);
 

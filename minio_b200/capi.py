@@ -60,6 +60,10 @@ def lib():
     L.mec_decode.restype = i64
     L.mec_decode.argtypes = [vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
     L.mec_heal.argtypes = [vp, vp, i64, vp]
+    L.mec_decode_prefer.restype = i64
+    L.mec_decode_prefer.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
+    L.mec_get_stat.restype = i64
+    L.mec_get_stat.argtypes = [vp, C.c_char_p]
     L.mec_bitrot_verify.argtypes = [vp, vp, i64, i64]
     L.mec_encode_whole.restype = i64
     L.mec_encode_whole.argtypes = [vp, vp, i64, vp, vp, i32]
@@ -174,11 +178,16 @@ class Codec:
             raise MecError(rc, "mec_encode")
         return files
 
-    def decode(self, files, offset, length, total):
+    def stat(self, name):
+        return lib().mec_get_stat(self.h, name.encode())
+
+    def decode(self, files, offset, length, total, prefer=None):
         files = [None if f is None else _u8(f) for f in files]
         dst = np.zeros(max(length, 1), dtype=np.uint8)
         hint = C.c_int(0)
-        rc = lib().mec_decode(self.h, _ptrs(files), offset, length, total, dst.ctypes.data, C.byref(hint))
+        pf = None if prefer is None else np.asarray(prefer, dtype=np.uint8)
+        rc = lib().mec_decode_prefer(self.h, _ptrs(files), None if pf is None else pf.ctypes.data, offset, length, total,
+                                     dst.ctypes.data, C.byref(hint))
         if rc < 0:
             raise MecError(rc, "mec_decode")
         return dst[:length], hint.value

@@ -11,6 +11,12 @@
 #include "../../include/minio_ec.h"
 #include "ec_engine.h"
 #include "whole_hash.cuh"
+#include <nvtx3/nvToolsExt.h>
+
+struct NvtxRange {
+  explicit NvtxRange(const char* n) { nvtxRangePushA(n); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
 
 using namespace mec;
 
@@ -45,6 +51,8 @@ struct mec_codec {
   Slot slots[kSlots];
   DevBuf in_files[kMaxShards];  // reconstruct: staged survivor frames, indexed by shard number
   DevBuf flags;
+  // boundary counters (mec_get_stat)
+  int64_t st_blocks_encoded = 0, st_blocks_read = 0, st_shards_rebuilt = 0, st_corrupt = 0, st_h2d = 0, st_d2h = 0;
   int64_t S() const { return ceil_frac(block_size, k); }
 };
 
@@ -145,6 +153,19 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else return MEC_ERR_INVALID_ARGUMENT;
   return MEC_OK;
 }
+extern "C" int64_t mec_get_stat(const mec_codec* c, const char* name) {
+  if (!c || !name) return -1;
+  if (!strcmp(name, "launches")) return c->eng ? c->eng->launches() : 0;
+  if (!strcmp(name, "blocks_encoded")) return c->st_blocks_encoded;
+  if (!strcmp(name, "blocks_read")) return c->st_blocks_read;
+  if (!strcmp(name, "shards_rebuilt")) return c->st_shards_rebuilt;
+  if (!strcmp(name, "corrupt_shards")) return c->st_corrupt;
+  if (!strcmp(name, "bytes_h2d")) return c->st_h2d;
+  if (!strcmp(name, "bytes_d2h")) return c->st_d2h;
+  if (!strcmp(name, "jit_compiles")) return c->eng ? c->eng->jit_compiles() : 0;
+  if (!strcmp(name, "jit_ms")) return c->eng ? static_cast<int64_t>(c->eng->jit_seconds() * 1e3) : 0;
+  return -1;
+}
 extern "C" int64_t mec_launch_count(const mec_codec* c) { return (c && c->eng) ? c->eng->launches() : 0; }
 
 static int require_streaming(mec_codec* c) {
@@ -190,6 +211,7 @@ static int encode_device_locked(mec_codec* c, const uint8_t* d_src, int64_t len,
 
 extern "C" int mec_encode_blocks_device(mec_codec* c, const uint8_t* d_src, int64_t len, uint8_t* d_parity,
                                         int64_t parity_pitch, uint8_t* d_digests, void* stream) {
+  NvtxRange nvtx("mec_encode_blocks_device");
   if (!c || len < 0) return MEC_ERR_INVALID_ARGUMENT;
   int rc;
   if (d_digests == nullptr) {  // parity only (whole-file bitrot algorithms hash separately, mec_whole_hash_device)
@@ -211,6 +233,7 @@ static int64_t pick_chunk_blocks(const mec_codec* c) {
 }
 
 extern "C" int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* parity, uint8_t* digests) {
+  NvtxRange nvtx("mec_encode_blocks");
   if (!c || len < 0) return MEC_ERR_INVALID_ARGUMENT;
   int rc = require_streaming(c);
   if (rc) return rc;
@@ -247,6 +270,9 @@ extern "C" int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, 
                                 cudaMemcpyDeviceToHost, s.st));
   }
   for (auto& s : c->slots) MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+  c->st_blocks_encoded += nall;
+  c->st_h2d += len;
+  c->st_d2h += nall * (c->m * S + c->n * 32);
   return MEC_OK;
 }
 
@@ -342,7 +368,9 @@ static int launch_reconstruct(mec_codec* c, const FrameGeom& g, int64_t cur, con
 
 // Core of Decode/Heal: frames[i] point at the first frame of the range (host), out[i] likewise.
 static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const FrameGeom& g, const uint8_t* want,
-                             int data_only, uint8_t* const* out, uint8_t* corrupt, uint8_t* alive /*n, in/out*/) {
+                             int data_only, uint8_t* const* out, uint8_t* corrupt, uint8_t* alive /*n, in/out*/,
+                             const uint8_t* prefer = nullptr) {
+  NvtxRange nvtx("mec_reconstruct_range");
   const int k = c->k, n = c->n;
   MEC_CUDA_OK(cudaSetDevice(c->device));
   cudaStream_t st = c->slots[0].st;
@@ -352,8 +380,22 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
   while (cur < g.nblocks) {
     // parallelReader.Read: first k alive readers in index order (cmd/erasure-decode.go:145-221)
     int chosen[kMaxShards], nch = 0;
-    for (int i = 0; i < n && nch < k; i++)
-      if (alive[i]) chosen[nch++] = i;
+    if (prefer) {  // preferReaders (cmd/erasure-decode.go:92-123): preferred readers are swapped to the front
+      int order[kMaxShards], next = 0;
+      for (int i = 0; i < n; i++) order[i] = i;
+      for (int i = 0; i < n; i++) {
+        if (!prefer[i] || frames[i] == nullptr) continue;
+        if (i == next) { next++; continue; }
+        std::swap(order[next], order[i]);
+        next++;
+      }
+      for (int q = 0; q < n && nch < k; q++)
+        if (alive[order[q]]) chosen[nch++] = order[q];
+      std::sort(chosen, chosen + nch);  // decode rows are defined on ascending shard indices
+    } else {
+      for (int i = 0; i < n && nch < k; i++)
+        if (alive[i]) chosen[nch++] = i;
+    }
     if (nch < k) return MEC_ERR_READ_QUORUM;
     std::vector<uint8_t> present(n, 0);
     for (int t = 0; t < k; t++) present[chosen[t]] = 1;
@@ -427,8 +469,11 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
         if (flags[static_cast<size_t>(bad * k + t)]) {
           alive[chosen[t]] = 0;
           if (corrupt) corrupt[chosen[t]] = 1;
+          c->st_corrupt++;
         }
     }
+    c->st_blocks_read += good;
+    c->st_shards_rebuilt += good * r;
     cur += good;
   }
   return MEC_OK;
@@ -492,6 +537,12 @@ extern "C" int mec_reconstruct_frames(mec_codec* c, const uint8_t* const* frames
 
 extern "C" int64_t mec_decode(mec_codec* c, const uint8_t* const* files, int64_t offset, int64_t length,
                               int64_t total, uint8_t* dst, int* heal_hint) {
+  return mec_decode_prefer(c, files, nullptr, offset, length, total, dst, heal_hint);
+}
+
+extern "C" int64_t mec_decode_prefer(mec_codec* c, const uint8_t* const* files, const uint8_t* prefer, int64_t offset,
+                                     int64_t length, int64_t total, uint8_t* dst, int* heal_hint) {
+  NvtxRange nvtx("mec_decode");
   if (heal_hint) *heal_hint = 0;
   if (!c || !files) return MEC_ERR_INVALID_ARGUMENT;
   if (offset < 0 || length < 0) return MEC_ERR_INVALID_ARGUMENT;      // cmd/erasure-decode.go:240-242
@@ -520,7 +571,7 @@ extern "C" int64_t mec_decode(mec_codec* c, const uint8_t* const* files, int64_t
   std::vector<std::vector<uint8_t>> tmp(k);
   std::vector<uint8_t*> out(n, nullptr);
   for (int i = 0; i < k; i++) { tmp[i].resize(static_cast<size_t>(g.file_bytes())); out[i] = tmp[i].data(); }
-  rc = reconstruct_range(c, in.data(), g, want.data(), 1, out.data(), corrupt.data(), alive.data());
+  rc = reconstruct_range(c, in.data(), g, want.data(), 1, out.data(), corrupt.data(), alive.data(), prefer);
   if (rc) return rc;
   // writeDataBlocks (cmd/erasure-utils.go:42) per block
   int64_t written = 0;
@@ -549,6 +600,7 @@ extern "C" int64_t mec_decode(mec_codec* c, const uint8_t* const* files, int64_t
 }
 
 extern "C" int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total, uint8_t* const* out_files) {
+  NvtxRange nvtx("mec_heal");
   if (!c || !files || !out_files) return MEC_ERR_INVALID_ARGUMENT;
   int rc = require_streaming(c);
   if (rc) return rc;

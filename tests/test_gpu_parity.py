@@ -466,3 +466,26 @@ def test_concurrent_callers(mb, oracle):
     shared.close()
     for c in own:
         c.close()
+
+
+def test_prefer_readers_and_stats(mb, oracle):
+    """parallelReader.preferReaders (cmd/erasure-decode.go:92-123): preferred readers are read first; a corrupt shard on a
+    non-preferred drive is then never touched, on a preferred drive it is detected.  Also the boundary counters."""
+    k, m, bs, size = 4, 4, MiB, 3 * MiB + 11
+    data = rand(size, 21)
+    files, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    bad = [f.copy() for f in files]
+    bad[1][5000] ^= 0x40                       # data shard 1 is corrupt
+    c = mb.Codec(k, m, bs)
+    out, hint = c.decode(bad, 0, size, size)   # default order reads shards 0..3 -> detects it
+    assert np.array_equal(out, data) and hint == -7
+    assert c.stat("corrupt_shards") == 1
+    out, hint = c.decode(bad, 0, size, size, prefer=[0, 0, 0, 0, 1, 1, 1, 1])   # parity drives are "local": shard 1 never read
+    assert np.array_equal(out, data) and hint == 0
+    out, hint = c.decode(bad, 0, size, size, prefer=[0, 1, 0, 0, 0, 0, 1, 0])   # swap order [1,6,2,3,...]: reads 1,6,2,3
+    assert np.array_equal(out, data) and hint == -7
+    assert c.stat("blocks_read") > 0 and c.stat("shards_rebuilt") > 0 and c.stat("launches") == c.launches
+    assert c.stat("no-such-counter") == -1
+    c.encode_blocks(data)
+    assert c.stat("blocks_encoded") == 4 and c.stat("bytes_h2d") == size
+    c.close()
