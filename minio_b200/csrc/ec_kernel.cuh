@@ -465,7 +465,12 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
       } else {
         __syncthreads();  // (A) aligned + output tiles complete; raw tile fully consumed
         if (i + 1 < ntiles) {  // refill the raw tile while the hash threads work on the aligned one
-          if constexpr (USE_TMA) {
+          if constexpr (USE_TMA && ROWS3D) {
+            if (warp0) {  // a single request per tile: no point in making every warp walk the issue code
+              if (elect_one()) issue_tile_at(i + 1, b0, nb, 0, 1);
+              __syncwarp();
+            }
+          } else if constexpr (USE_TMA) {
             if (elect_one()) issue_tile_at(i + 1, b0, nb, warp_id, nthr >> 5);
             __syncwarp();
           } else {
