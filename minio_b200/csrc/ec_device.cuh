@@ -204,12 +204,12 @@ __device__ __forceinline__ void hh_zipper(uint64_t hi, uint64_t lo, uint64_t& z1
   const uint32_t v0l = static_cast<uint32_t>(lo), v0h = static_cast<uint32_t>(lo >> 32);
   const uint32_t v1l = static_cast<uint32_t>(hi), v1h = static_cast<uint32_t>(hi >> 32);
   // add0 += [v0.b3, v1.b4, v0.b2, v0.b5 | v1.b6, v0.b1, v1.b7, v0.b0]
-  const uint32_t t0 = prmt(v0l, v0h, 0x5203u);
-  const uint32_t a0l = prmt(t0, v1h, 0x3240u);
-  const uint32_t a0h = prmt(v0l, v1h, 0x0716u);
   // add1 += [v1.b3, v0.b4, v1.b2, v1.b5 | v1.b1, v0.b6, v1.b0, v0.b7]
-  const uint32_t t1 = prmt(v1l, v1h, 0x5203u);
-  const uint32_t a1l = prmt(t1, v0h, 0x3240u);
+  // the four bytes both low words take from the high halves are gathered once: 5 PRMTs instead of 6
+  const uint32_t x = prmt(v0h, v1h, 0x5041u);  // [v0.b5, v1.b4, v0.b4, v1.b5]
+  const uint32_t a0l = prmt(v0l, x, 0x4253u);
+  const uint32_t a0h = prmt(v0l, v1h, 0x0716u);
+  const uint32_t a1l = prmt(v1l, x, 0x7263u);
   const uint32_t a1h = prmt(v1l, v0h, 0x7061u);
   z0 = pack64(a0l, a0h);
   z1 = pack64(a1l, a1h);
