@@ -102,9 +102,14 @@ int mec_reconstruct_frames(mec_codec* c, const uint8_t* const* frames, int64_t n
  * d_out + (b*r + q)*out_pitch (q = rank of i among the rebuilt shards) and its digest written to
  * d_digests[(b*(k+r) + k + q)*32]; digests of the k shards read land in d_digests[(b*(k+r) + t)*32] and
  * d_corrupt[b*k + t] is set when frame t of block b fails its stored digest.  All nblocks are full blocks.
+ * `flags`: MEC_RECONSTRUCT_DATA_ONLY = ReconstructData semantics (parity never rebuilt);
+ * MEC_RECONSTRUCT_NO_OUTPUT_DIGESTS = the rebuilt shards are not hashed (GetObject consumes their bytes only,
+ * cmd/erasure-decode.go:283-289; the k shards read are still hashed and checked), their digest slots stay untouched.
  * Asynchronous on `cuda_stream`; the fail-over policy stays with the caller (see mec_reconstruct_frames). */
+#define MEC_RECONSTRUCT_DATA_ONLY 1
+#define MEC_RECONSTRUCT_NO_OUTPUT_DIGESTS 2
 int mec_reconstruct_device(mec_codec* c, const uint8_t* const* d_frames, int64_t frame_pitch, int64_t nblocks,
-                           const uint8_t* want, int data_only, uint8_t* d_out, int64_t out_pitch,
+                           const uint8_t* want, int flags, uint8_t* d_out, int64_t out_pitch,
                            uint8_t* d_digests, uint8_t* d_corrupt, void* cuda_stream);
 
 /* ---- whole-part drivers ------------------------------------------------------------------- */

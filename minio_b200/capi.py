@@ -159,10 +159,11 @@ class Codec:
             raise MecError(rc, "mec_encode_blocks_device")
 
     def reconstruct_device(self, d_frames, frame_pitch, nblocks, want, data_only, d_out, out_pitch, d_digests, d_corrupt, stream=0):
-        """d_frames: list of k+m device pointers (0/None = unavailable)."""
+        """d_frames: list of k+m device pointers (0/None = unavailable).  data_only: bool, or the MEC_RECONSTRUCT_* flag bits
+        (1 = data only, 2 = no digests for the rebuilt shards)."""
         arr = (C.c_void_p * self.n)(*[(p or None) for p in d_frames])
         want = np.asarray(want, dtype=np.uint8)
-        rc = lib().mec_reconstruct_device(self.h, arr, frame_pitch, nblocks, want.ctypes.data, 1 if data_only else 0,
+        rc = lib().mec_reconstruct_device(self.h, arr, frame_pitch, nblocks, want.ctypes.data, int(data_only),
                                           d_out, out_pitch, d_digests, d_corrupt, stream)
         if rc:
             raise MecError(rc, "mec_reconstruct_device")

@@ -338,9 +338,9 @@ static int stage_frames(const uint8_t* host, void* dev, const FrameGeom& g, cuda
 // d_out rows: (b*r + q); digests [b][k + r]; flags [b][k].
 static int launch_reconstruct(mec_codec* c, const FrameGeom& g, int64_t cur, const int* chosen, int r,
                               const uint8_t* rows, uint8_t* d_out, int64_t pitch, uint8_t* d_dig, uint8_t* d_flags,
-                              cudaStream_t st) {
+                              cudaStream_t st, bool hash_outputs) {
   FusedDesc d;
-  d.k = c->k; d.r = r; d.coef = rows; d.static_encode = false; d.contiguous = false;
+  d.k = c->k; d.r = r; d.coef = rows; d.static_encode = false; d.contiguous = false; d.hash_outputs = hash_outputs;
   d.key = kMagicKey; d.out_pitch = pitch; d.expect_block_stride = g.dpitch(); d.in_block_stride = g.dpitch();
   // blocks [cur, g.nblocks) of the staged files; outputs are indexed from block `cur`
   const int64_t nfull_all = (g.last_len == g.S) ? g.nblocks : g.nblocks - 1;
@@ -369,7 +369,7 @@ static int launch_reconstruct(mec_codec* c, const FrameGeom& g, int64_t cur, con
 // Core of Decode/Heal: frames[i] point at the first frame of the range (host), out[i] likewise.
 static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const FrameGeom& g, const uint8_t* want,
                              int data_only, uint8_t* const* out, uint8_t* corrupt, uint8_t* alive /*n, in/out*/,
-                             const uint8_t* prefer = nullptr) {
+                             const uint8_t* prefer = nullptr, bool hash_outputs = true) {
   NvtxRange nvtx("mec_reconstruct_range");
   const int k = c->k, n = c->n;
   MEC_CUDA_OK(cudaSetDevice(c->device));
@@ -424,7 +424,7 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
     if ((rc = c->flags.ensure(static_cast<size_t>(sub.nblocks * k)))) return rc;
     MEC_CUDA_OK(cudaMemsetAsync(c->flags.p, 0, static_cast<size_t>(sub.nblocks * k), st));
     rc = launch_reconstruct(c, g, cur, chosen, r, rows.data(), static_cast<uint8_t*>(s.out.p), pitch,
-                            static_cast<uint8_t*>(s.dig.p), static_cast<uint8_t*>(c->flags.p), st);
+                            static_cast<uint8_t*>(s.dig.p), static_cast<uint8_t*>(c->flags.p), st, hash_outputs);
     if (rc) return rc;
     std::vector<uint8_t> flags(static_cast<size_t>(sub.nblocks * k));
     MEC_CUDA_OK(cudaMemcpyAsync(flags.data(), c->flags.p, flags.size(), cudaMemcpyDeviceToHost, st));
@@ -480,9 +480,10 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
 }
 
 extern "C" int mec_reconstruct_device(mec_codec* c, const uint8_t* const* d_frames, int64_t frame_pitch, int64_t nblocks,
-                                      const uint8_t* want, int data_only, uint8_t* d_out, int64_t out_pitch,
+                                      const uint8_t* want, int flags, uint8_t* d_out, int64_t out_pitch,
                                       uint8_t* d_digests, uint8_t* d_corrupt, void* stream) {
   if (!c || !d_frames || !want || nblocks < 0) return MEC_ERR_INVALID_ARGUMENT;
+  const int data_only = flags & MEC_RECONSTRUCT_DATA_ONLY;
   int rc = require_streaming(c);
   if (rc) return rc;
   if (nblocks == 0) return MEC_OK;
@@ -516,6 +517,7 @@ extern "C" int mec_reconstruct_device(mec_codec* c, const uint8_t* const* d_fram
     d.in_ptr[t] = base + 32;
   }
   d.out = d_out; d.out_pitch = out_pitch; d.digests = d_digests; d.corrupt = d_corrupt;
+  d.hash_outputs = !(flags & MEC_RECONSTRUCT_NO_OUTPUT_DIGESTS);
   return c->eng->launch_fused(d, c->opt, static_cast<cudaStream_t>(stream));
 }
 
@@ -571,7 +573,8 @@ extern "C" int64_t mec_decode_prefer(mec_codec* c, const uint8_t* const* files, 
   std::vector<std::vector<uint8_t>> tmp(k);
   std::vector<uint8_t*> out(n, nullptr);
   for (int i = 0; i < k; i++) { tmp[i].resize(static_cast<size_t>(g.file_bytes())); out[i] = tmp[i].data(); }
-  rc = reconstruct_range(c, in.data(), g, want.data(), 1, out.data(), corrupt.data(), alive.data(), prefer);
+  // GetObject only consumes the data bytes of the rebuilt shards: their digests are not computed
+  rc = reconstruct_range(c, in.data(), g, want.data(), 1, out.data(), corrupt.data(), alive.data(), prefer, false);
   if (rc) return rc;
   // writeDataBlocks (cmd/erasure-utils.go:42) per block
   int64_t written = 0;

@@ -244,6 +244,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   p.out = d.out;
   p.out_pitch = d.out_pitch;
   p.digests = d.digests;
+  p.nhash = d.hash_outputs ? d.k + d.r : d.k;
   p.corrupt = d.corrupt;
   p.expect_block_stride = d.expect_block_stride;
   for (int t = 0; t < d.k; t++) p.expect_ptr[t] = d.expect_ptr[t];
@@ -374,7 +375,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     const int64_t in_bytes = d.nblocks * static_cast<int64_t>(d.S) * d.k;
     if (opt.jit == 1 || (opt.jit < 0 && in_bytes >= (256ll << 20))) {
       void* jk = nullptr;
-      if (!d.contiguous && !any_misaligned) jk = jit_kernel(d.k, d.r, d.coef, 0, 0, false);            // decode rows, aligned staging
+      if (!d.contiguous && !any_misaligned) jk = jit_kernel(d.k, d.r, d.coef, 0, eb == kStaticEb ? kStaticEb : 0, false);  // decode rows, aligned staging
       else if (d.contiguous && eb == kStaticEb) jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false);  // any (k, m) encode
       if (jk) { kfn = jk; jitted = true; }
     }

@@ -40,6 +40,7 @@ struct FusedDesc {
   uint8_t* out = nullptr;
   int64_t out_pitch = 0;
   uint8_t* digests = nullptr;      // nullptr: skip hashing entirely
+  bool hash_outputs = true;        // false: only the k inputs are hashed (GET path: reconstructed data needs no digest)
   const uint8_t* expect_ptr[kMaxK] = {};
   int64_t expect_block_stride = 0;
   uint8_t* corrupt = nullptr;

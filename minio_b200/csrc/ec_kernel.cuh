@@ -45,6 +45,7 @@ struct FusedParams {
   int tiles_3d;                    // ROWS3D: tiles [0, tiles_3d) of a shard are fetched with one 3-D request
   int raw_pitch;                   // bytes between erasure blocks inside a raw row group (272; 384 when every row is its own TMA box)
   int64_t nblocks;
+  int nhash;                       // streams hashed per erasure block: k + r, or k when the outputs carry no digest
   int32_t S;                       // shard bytes per erasure block
   int32_t in_c0_block_step;        // kLoadTmaPerInput: bytes between blocks in an input stream (multiple of 16)
   int32_t in_c0[kMaxK];            // TMA: 16B-aligned byte coordinate of input t (block 0, x = 0)
@@ -184,10 +185,11 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
   __syncthreads();
 
   // ---- HighwayHash thread identity: 2 threads per stream
-  const bool hh_thread = p.digests != nullptr && tid < 2 * nstreams * eb;
+  const int nhash = AUTO ? nstreams : p.nhash;
+  const bool hh_thread = p.digests != nullptr && tid < 2 * nhash * eb;
   const int sl = tid >> 1, h = tid & 1;
-  const int e_hh = hh_thread ? sl / nstreams : 0;
-  const int srow = hh_thread ? sl % nstreams : 0;
+  const int e_hh = hh_thread ? sl / nhash : 0;
+  const int srow = hh_thread ? sl % nhash : 0;
   const bool is_out = srow >= k;
   const uint8_t* hh_row = is_out ? s_par + static_cast<uint32_t>(e_hh * r + (srow - k)) * kRowPitch
                                  : s_clean + static_cast<uint32_t>(e_hh * k + srow) * kRowPitch;

@@ -327,6 +327,59 @@ def test_device_resident_large_roundtrip(mb, oracle):
     c.close()
 
 
+@pytest.mark.parametrize("jit", [0, 1])
+@pytest.mark.parametrize("erased", [[0, 1, 2, 3], [5], [2, 13]])
+def test_reconstruct_device_without_output_digests(mb, oracle, erased, jit):
+    """GetObject shape (cmd/erasure-decode.go:283-289): the shards read are hashed and checked, the rebuilt data shards are
+    only written — MEC_RECONSTRUCT_NO_OUTPUT_DIGESTS leaves their digest slots untouched and the bytes identical."""
+    import torch
+    k, m, bs, nblocks = 12, 4, MiB, 24
+    n, S = k + m, 87382
+    dev = torch.device("cuda:0")
+    data = rand(nblocks * bs, 4242)
+    files, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    fp = (32 + S + 15) // 16 * 16
+    frames = []
+    for i in range(n):
+        f = torch.zeros((nblocks, fp), dtype=torch.uint8, device=dev)
+        f[:, :32 + S] = torch.from_numpy(files[i].reshape(nblocks, 32 + S)).to(dev)
+        frames.append(f)
+    frames[7][3, 40] ^= 0x10  # one flipped bit in a shard that is read
+    c = mb.Codec(k, m, bs)
+    c.set_option("jit", jit)
+    want = [1 if i in erased else 0 for i in range(n)]
+    ptrs = [0 if i in erased else frames[i].data_ptr() for i in range(n)]
+    targets = [i for i in erased if i < k]
+    r = len(targets)
+    opitch = (S + 15) // 16 * 16
+    for flags in (1, 3):
+        out = torch.zeros((nblocks * r, opitch), dtype=torch.uint8, device=dev)
+        dig = torch.full((nblocks, k + r, 32), 0xA5, dtype=torch.uint8, device=dev)
+        cor = torch.zeros((nblocks, k), dtype=torch.uint8, device=dev)
+        c.reconstruct_device(ptrs, fp, nblocks, want, flags, out.data_ptr(), opitch, dig.data_ptr(), cor.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        chosen = [i for i in range(n) if i not in erased][:k]
+        h_cor = cor.cpu().numpy()
+        bad = np.argwhere(h_cor)
+        assert bad.tolist() == [[3, chosen.index(7)]]
+        h_out = out.cpu().numpy().reshape(nblocks, r, opitch)
+        h_dig = dig.cpu().numpy()
+        for b in range(nblocks):
+            if b == 3:
+                continue  # rebuilt from a corrupt frame: the caller drops this block (fail-over is the caller's job)
+            for q, i in enumerate(targets):
+                ref = files[i].reshape(nblocks, 32 + S)[b]
+                assert np.array_equal(h_out[b, q, :S], ref[32:]), (flags, b, i)
+                if flags & 2:
+                    assert (h_dig[b, k + q] == 0xA5).all()
+                else:
+                    assert h_dig[b, k + q].tobytes() == ref[:32].tobytes()
+            for t, i in enumerate(chosen):
+                if i != 7 or b != 3:
+                    assert h_dig[b, t].tobytes() == files[i].reshape(nblocks, 32 + S)[b, :32].tobytes()
+    c.close()
+
+
 @pytest.mark.parametrize("k,m,stale", [(12, 4, [0, 1, 2, 3]), (12, 4, [1, 5, 12, 15]), (16, 4, [0, 7, 16, 19]), (8, 8, [0, 1, 2, 3, 8, 9, 10, 11]), (4, 2, [1, 4])])
 def test_heal_with_runtime_specialised_kernels(mb, oracle, k, m, stale):
     """Decode matrices compiled with NVRTC at run time (option jit=1) must give the same bytes as the generic kernel."""
