@@ -113,10 +113,10 @@ static NvrtcApi& nvrtc_api() {
 static std::mutex g_jit_mu;
 static std::vector<std::pair<std::string, void*>> g_jit_cache;
 
-void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d) {
+void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out) {
   std::string key(reinterpret_cast<const char*>(coef), static_cast<size_t>(k) * r);
   key = "d" + std::to_string(device_) + ":" + std::to_string(k) + "x" + std::to_string(r) + "a" + std::to_string(align) + "e" +
-        std::to_string(eb_t) + (rows3d ? "3" : "2") + ":" + key;
+        std::to_string(eb_t) + (rows3d ? "3" : "2") + (hash_out ? "h" : "n") + ":" + key;
   std::lock_guard<std::mutex> lk(g_jit_mu);
   for (auto& e : g_jit_cache)
     if (e.first == key) return e.second;
@@ -131,7 +131,8 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t,
       for (int t = 0; t < k; t++) src += std::to_string(coef[static_cast<size_t>(j) * k + t]) + (t + 1 < k ? "," : "");
       src += j + 1 < r ? "}," : "}";
     }
-    src += "};\n    return m[j][t]; } };\nstruct GfJit { static constexpr bool kIsStatic = true; static constexpr int K = JitMat::K, R = JitMat::R; using Mat = JitMat; };\n}\n";
+    src += "};\n    return m[j][t]; } };\nstruct GfJit { static constexpr bool kIsStatic = true; static constexpr int K = JitMat::K, R = JitMat::R, kHashOut = " +
+           std::string(hash_out ? "1" : "0") + "; using Mat = JitMat; };\n}\n";
     const char* names[] = {"rtc_compat.h", "gf256.h", "ec_device.cuh", "ec_kernel.cuh"};
     const char* bodies[] = {kJitHdr_rtc_compat_h, kJitHdr_gf256_h, kJitHdr_ec_device_cuh, kJitHdr_ec_kernel_cuh};
     nvrtcProgram prog = nullptr;
@@ -267,7 +268,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
 
   // ---- static / dynamic GF
   const StaticEntry* se = nullptr;
-  if (d.static_encode && d.contiguous && !opt.force_dynamic)
+  if (d.static_encode && d.contiguous && d.hash_outputs && !opt.force_dynamic)
     for (const auto& ent : kStaticTable)
       if (ent.k == d.k && ent.m == d.r) se = &ent;
   if (!se) {
@@ -375,8 +376,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     const int64_t in_bytes = d.nblocks * static_cast<int64_t>(d.S) * d.k;
     if (opt.jit == 1 || (opt.jit < 0 && in_bytes >= (256ll << 20))) {
       void* jk = nullptr;
-      if (!d.contiguous && !any_misaligned) jk = jit_kernel(d.k, d.r, d.coef, 0, eb == kStaticEb ? kStaticEb : 0, false);  // decode rows, aligned staging
-      else if (d.contiguous && eb == kStaticEb) jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false);  // any (k, m) encode
+      if (!d.contiguous && !any_misaligned) jk = jit_kernel(d.k, d.r, d.coef, 0, eb == kStaticEb ? kStaticEb : 0, false, d.hash_outputs);  // decode rows, aligned staging
+      else if (d.contiguous && d.hash_outputs && eb == kStaticEb) jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false, true);  // any (k, m) encode
       if (jk) { kfn = jk; jitted = true; }
     }
   }

@@ -77,7 +77,7 @@ class Engine {
   void* encode_tiled_ = nullptr;  // cuTensorMapEncodeTiled
   int64_t launches_ = 0;
   // run-time specialised kernels, keyed by (k, r, matrix bytes)
-  void* jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d);
+  void* jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out);
   int64_t jit_compiles_ = 0;
   double jit_seconds_ = 0;
 };

@@ -68,17 +68,19 @@ template <int K_, int M_>
 struct GfStatic {
   static constexpr bool kIsStatic = true;
   static constexpr int K = K_, R = M_;
+  static constexpr int kHashOut = 1;  // outputs always carry a digest (encode)
   using Mat = EncodeMatrix<K_, M_>;
 };
 template <int RC_>  // rows of the runtime matrix handled per pass over the inputs (1, 2 or 4)
 struct GfDynamic {
   static constexpr bool kIsStatic = false;
   static constexpr int K = 0, R = 0, RC = RC_;
+  static constexpr int kHashOut = -1;  // FusedParams::nhash decides at run time
 };
 
-__host__ __device__ inline uint32_t raw_group_bytes(int eb, int raw_pitch) { return (static_cast<uint32_t>(eb) * raw_pitch + 127u) & ~127u; }
+__host__ __device__ constexpr uint32_t raw_group_bytes(int eb, int raw_pitch) { return (static_cast<uint32_t>(eb) * raw_pitch + 127u) & ~127u; }
 
-__host__ __device__ inline uint32_t fused_smem_bytes(int k, int r, int eb, int raw_pitch, bool dynamic_gf) {
+__host__ __device__ constexpr uint32_t fused_smem_bytes(int k, int r, int eb, int raw_pitch, bool dynamic_gf) {
   uint32_t b = 128 + 128;  // alignment slack + barrier
   b += static_cast<uint32_t>(k) * raw_group_bytes(eb, raw_pitch);
   b += static_cast<uint32_t>(k + (r > 0 ? r : 0)) * eb * kRowPitch;
@@ -133,8 +135,25 @@ __device__ __forceinline__ uint2 load_col_rt(const uint8_t* row, uint32_t a) {
 // ROWS3D: all k rows x eb blocks of a tile arrive with ONE 3-D TMA request (x, block, row) instead of k requests;
 // only the last tiles of a shard, whose box would cross the row stride, fall back to per-row requests (which also
 // provide Split's zero padding through out-of-bounds fill).  Needs a compile-time ALIGN and EB_T.
+// Launch bounds: with a compile-time CTA shape the register budget follows the CTAs that fit anyway — 72 registers
+// when seven 128-thread CTAs fit in shared memory, 80 when shared memory stops at six.  Left alone, ptxas / NVRTC
+// drift between 72 and 80 registers from one build to the next and lose a CTA per SM.
+template <class GF, int EB_T>
+__host__ __device__ constexpr int fused_max_threads() {
+  return (EB_T > 0 && GF::K > 0) ? ((2 * (GF::K + GF::R) * EB_T + 31) / 32 * 32) : 256;
+}
+template <class GF, int ALIGN, int EB_T, bool ROWS3D>
+__host__ __device__ constexpr int fused_min_blocks() {
+  if (!(EB_T > 0 && GF::K > 0)) return MEC_MIN_BLOCKS;
+  constexpr int t = fused_max_threads<GF, EB_T>();
+  const int by_regs = 65536 / (72 * t);
+  const int raw = ROWS3D ? raw_row_3d(GF::K > 0 ? GF::K : 1, ALIGN > 0 ? ALIGN : 0, EB_T > 0 ? EB_T : 1) : kRawRow;
+  const int by_smem = 233472 / (static_cast<int>(fused_smem_bytes(GF::K, GF::R, EB_T, raw, false)) + 1024);
+  const int b = by_regs < by_smem ? by_regs : by_smem;
+  return b > 0 ? b : 1;
+}
 template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO, bool ROWS3D = false>
-__global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
+__global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_blocks<GF, ALIGN, EB_T, ROWS3D>())) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
   // MEC_PIPE2: software-pipelined loop (TMA lead of a whole tile).  Measured: removes the mbarrier wait stall but costs
   // ~3% more instructions; net -1.5% on RS(12,4) at full occupancy, so it is off by default.
@@ -185,7 +204,7 @@ __global__ void __launch_bounds__(256, MEC_MIN_BLOCKS) fused_rs_hh_kernel(const 
   __syncthreads();
 
   // ---- HighwayHash thread identity: 2 threads per stream
-  const int nhash = AUTO ? nstreams : p.nhash;
+  const int nhash = (AUTO || GF::kHashOut == 1) ? nstreams : (GF::kHashOut == 0 ? k : p.nhash);
   const bool hh_thread = p.digests != nullptr && tid < 2 * nhash * eb;
   const int sl = tid >> 1, h = tid & 1;
   const int e_hh = hh_thread ? sl / nhash : 0;

@@ -193,6 +193,11 @@ def sha256_sweep(k, m, sizes, total_bytes):
 if __name__ == "__main__":
     MiB = 1 << 20
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "jit":
+        for _ in range(3):
+            jit_encode_case(10, 4, MiB, 4096)
+        jit_encode_case(10, 4, MiB, 8192)
+        sys.exit(0)
     if only == "3a":   # one case, e.g. under ncu
         reconstruct_case("3a: RS(12,4) GetObject shape, data shards {0,1,2,3} erased", 12, 4, MiB, int(sys.argv[2]) if len(sys.argv) > 2 else 3552, {0, 1, 2, 3}, 3, 3)
         sys.exit(0)
