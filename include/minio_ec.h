@@ -172,10 +172,14 @@ int mec_hh256_batch(mec_codec* c, const uint8_t* msgs, int64_t msg_len, int64_t 
 /* erasureSelfTest + bitrotSelfTest (cmd/erasure-coding.go:149, cmd/bitrot.go:224) on the GPU. */
 int mec_selftest(int device);
 
-/* tuning knobs for benchmarks/tests (erasure blocks per CTA, loader, GF specialisation) */
+/* tuning knobs for benchmarks/tests (erasure blocks per CTA, loader, GF specialisation).
+ * "jit": run-time specialisation of decode matrices / uncompiled (k, m) geometries with NVRTC, cached per process:
+ *   -1 (default) a pattern that has been seen with 32 MiB of input is compiled on a background thread; calls that
+ *      arrive before it is ready run the generic runtime-matrix kernel — no request ever waits for the compiler;
+ *    1 compile (or wait for the background compile) inside the call — tests and benchmarks;  0 never specialise. */
 int mec_set_option(mec_codec* c, const char* name, int64_t value);
 /* Boundary counters (SURVEY §5 metrics row): name is one of "launches", "blocks_encoded", "blocks_read",
- * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms".  -1 for unknown names.
+ * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms" (both process-wide), "jit_launches".  -1 for unknown names.
  * Every ABI call is also wrapped in an NVTX range (visible in Nsight Systems) — the tracing hook of SURVEY §5. */
 int64_t mec_get_stat(const mec_codec* c, const char* name);
 /* number of kernels launched by this codec so far (bench.py's gpu_launches) */

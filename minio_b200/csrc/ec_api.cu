@@ -163,6 +163,7 @@ extern "C" int64_t mec_get_stat(const mec_codec* c, const char* name) {
   if (!strcmp(name, "bytes_h2d")) return c->st_h2d;
   if (!strcmp(name, "bytes_d2h")) return c->st_d2h;
   if (!strcmp(name, "jit_compiles")) return c->eng ? c->eng->jit_compiles() : 0;
+  if (!strcmp(name, "jit_launches")) return c->eng ? c->eng->jit_launches() : 0;
   if (!strcmp(name, "jit_ms")) return c->eng ? static_cast<int64_t>(c->eng->jit_seconds() * 1e3) : 0;
   return -1;
 }

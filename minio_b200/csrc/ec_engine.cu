@@ -5,6 +5,13 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 #include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 #include "../../include/minio_ec.h"
 #include "ec_engine.h"
 #include "jit_headers.inc"
@@ -110,71 +117,186 @@ static NvrtcApi& nvrtc_api() {
 
 // The cache is process-wide (per device): MinIO builds one Erasure per request (cmd/erasure-object.go:1371), so a
 // per-codec cache would recompile the same erasure pattern for every object of a heal sweep.
-static std::mutex g_jit_mu;
-static std::vector<std::pair<std::string, void*>> g_jit_cache;
+//
+// Policy.  A compile costs ≈0.4 s of one host core; the specialised kernel saves ≈1 ms per GiB over the generic one, so
+// stalling a request for it never pays inside that request.  In automatic mode (option jit = -1) a pattern is therefore
+// compiled on a background thread once it has been seen with kJitHeatBytes of input, the requests that arrive meanwhile
+// run the generic runtime-matrix kernel, and later requests pick the specialised kernel up from the cache.  jit = 1
+// compiles (or waits for the background compile) synchronously — tests and benchmarks; jit = 0 never specialises.
+namespace {
+constexpr int64_t kJitHeatBytes = 32ll << 20;
+enum JitState { kJitAbsent = 0, kJitCompiling, kJitReady, kJitFailed };
+struct JitSpec {
+  int device, k, r, align, eb_t;
+  bool rows3d, hash_out;
+  std::vector<uint8_t> coef;
+};
+struct JitEntry {
+  std::string key;
+  JitSpec spec;
+  int state = kJitAbsent;
+  void* kernel = nullptr;
+  int64_t heat = 0;
+};
+struct JitGlobals {
+  std::mutex mu;
+  std::condition_variable cv_done, cv_work;
+  std::vector<std::unique_ptr<JitEntry>> cache;
+  std::deque<JitEntry*> queue;
+  std::thread worker;
+  bool stop = false;
+  int64_t compiles = 0;
+  double seconds = 0;
+  ~JitGlobals() {
+    {
+      std::lock_guard<std::mutex> lk(mu);
+      stop = true;
+    }
+    cv_work.notify_all();
+    if (worker.joinable()) worker.join();
+  }
+};
+JitGlobals& jit_globals() {
+  static JitGlobals g;
+  return g;
+}
 
-void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out) {
+// NVRTC-instantiate the kernel template for one concrete matrix; returns a cudaKernel_t or nullptr
+void* compile_specialised(const JitSpec& sp) {
+  NvrtcApi& api = nvrtc_api();
+  if (!api.ok) return nullptr;
+  if (cudaSetDevice(sp.device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  const int k = sp.k, r = sp.r;
+  void* result = nullptr;
+  std::string src = "#include \"ec_kernel.cuh\"\nnamespace mec {\nstruct JitMat { static constexpr int K = " + std::to_string(k) +
+                    ", R = " + std::to_string(r) + ";\n  __host__ __device__ static constexpr uint8_t coef(int j, int t) {\n    constexpr uint8_t m[R][K] = {";
+  for (int j = 0; j < r; j++) {
+    src += "{";
+    for (int t = 0; t < k; t++) src += std::to_string(sp.coef[static_cast<size_t>(j) * k + t]) + (t + 1 < k ? "," : "");
+    src += j + 1 < r ? "}," : "}";
+  }
+  src += "};\n    return m[j][t]; } };\nstruct GfJit { static constexpr bool kIsStatic = true; static constexpr int K = JitMat::K, R = JitMat::R, kHashOut = " +
+         std::string(sp.hash_out ? "1" : "0") + "; using Mat = JitMat; };\n}\n";
+  const char* names[] = {"rtc_compat.h", "gf256.h", "ec_device.cuh", "ec_kernel.cuh"};
+  const char* bodies[] = {kJitHdr_rtc_compat_h, kJitHdr_gf256_h, kJitHdr_ec_device_cuh, kJitHdr_ec_kernel_cuh};
+  nvrtcProgram prog = nullptr;
+  const std::string expr_s = "mec::fused_rs_hh_kernel<mec::GfJit, true, " + std::to_string(sp.align) + ", " + std::to_string(sp.eb_t) +
+                             ", false, " + (sp.rows3d ? "true" : "false") + ">";
+  const char* expr = expr_s.c_str();
+  if (api.create(&prog, src.c_str(), "mec_jit.cu", 4, bodies, names) != NVRTC_SUCCESS) return nullptr;
+  api.add_name(prog, expr);
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
+                        "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
+                        "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS), "-DMEC_PIPE2=" MEC_STR(MEC_PIPE2),
+                        "-DMEC_GF_DIV=" MEC_STR(MEC_GF_DIV), "-DMEC_GF_GROUP=" MEC_STR(MEC_GF_GROUP),
+                        "-DMEC_FUSED_STEP=" MEC_STR(MEC_FUSED_STEP)};
+  nvrtcResult rc = api.compile(prog, 11, opts);
+  if (rc == NVRTC_SUCCESS) {
+    size_t sz = 0;
+    const char* lname = nullptr;
+    if (api.cubin_size(prog, &sz) == NVRTC_SUCCESS && sz > 0 && api.lowered(prog, expr, &lname) == NVRTC_SUCCESS) {
+      std::vector<char> cubin(sz);
+      api.cubin(prog, cubin.data());
+      cudaLibrary_t lib = nullptr;
+      cudaKernel_t kern = nullptr;
+      if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+          cudaLibraryGetKernel(&kern, lib, lname) == cudaSuccess)
+        result = reinterpret_cast<void*>(kern);
+      else
+        cudaGetLastError();
+    }
+  } else {
+    size_t ls = 0;
+    api.log_size(prog, &ls);
+    std::string log(ls, 0);
+    if (ls) api.log(prog, &log[0]);
+    set_last_error("NVRTC specialisation failed, using the runtime-matrix kernel: " + log.substr(0, 800));
+  }
+  api.destroy(&prog);
+  return result;
+}
+
+// compile `e` (state already kJitCompiling, mutex NOT held), publish the result
+void jit_run(JitGlobals& g, JitEntry* e) {
+  const auto t0 = std::chrono::steady_clock::now();
+  void* kern = compile_specialised(e->spec);
+  const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  {
+    std::lock_guard<std::mutex> lk(g.mu);
+    e->kernel = kern;
+    e->state = kern ? kJitReady : kJitFailed;  // failures are cached too: never retried, the generic kernel serves
+    g.compiles++;
+    g.seconds += sec;
+  }
+  g.cv_done.notify_all();
+}
+
+void jit_worker_main() {
+  JitGlobals& g = jit_globals();
+  for (;;) {
+    JitEntry* e = nullptr;
+    {
+      std::unique_lock<std::mutex> lk(g.mu);
+      g.cv_work.wait(lk, [&] { return g.stop || !g.queue.empty(); });
+      if (g.stop) return;
+      e = g.queue.front();
+      g.queue.pop_front();
+    }
+    jit_run(g, e);
+  }
+}
+}  // namespace
+
+int64_t Engine::jit_compiles() const {
+  JitGlobals& g = jit_globals();
+  std::lock_guard<std::mutex> lk(g.mu);
+  return g.compiles;
+}
+double Engine::jit_seconds() const {
+  JitGlobals& g = jit_globals();
+  std::lock_guard<std::mutex> lk(g.mu);
+  return g.seconds;
+}
+
+// mode 1: return the specialised kernel, compiling or waiting for it; mode -1: return it if it is ready, otherwise
+// account `in_bytes` to the pattern and hand it to the background worker once it is warm.
+void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out, int mode,
+                         int64_t in_bytes) {
   std::string key(reinterpret_cast<const char*>(coef), static_cast<size_t>(k) * r);
   key = "d" + std::to_string(device_) + ":" + std::to_string(k) + "x" + std::to_string(r) + "a" + std::to_string(align) + "e" +
         std::to_string(eb_t) + (rows3d ? "3" : "2") + (hash_out ? "h" : "n") + ":" + key;
-  std::lock_guard<std::mutex> lk(g_jit_mu);
-  for (auto& e : g_jit_cache)
-    if (e.first == key) return e.second;
-  NvrtcApi& api = nvrtc_api();
-  void* result = nullptr;
-  if (api.ok) {
-    const auto t0 = std::chrono::steady_clock::now();
-    std::string src = "#include \"ec_kernel.cuh\"\nnamespace mec {\nstruct JitMat { static constexpr int K = " + std::to_string(k) +
-                      ", R = " + std::to_string(r) + ";\n  __host__ __device__ static constexpr uint8_t coef(int j, int t) {\n    constexpr uint8_t m[R][K] = {";
-    for (int j = 0; j < r; j++) {
-      src += "{";
-      for (int t = 0; t < k; t++) src += std::to_string(coef[static_cast<size_t>(j) * k + t]) + (t + 1 < k ? "," : "");
-      src += j + 1 < r ? "}," : "}";
-    }
-    src += "};\n    return m[j][t]; } };\nstruct GfJit { static constexpr bool kIsStatic = true; static constexpr int K = JitMat::K, R = JitMat::R, kHashOut = " +
-           std::string(hash_out ? "1" : "0") + "; using Mat = JitMat; };\n}\n";
-    const char* names[] = {"rtc_compat.h", "gf256.h", "ec_device.cuh", "ec_kernel.cuh"};
-    const char* bodies[] = {kJitHdr_rtc_compat_h, kJitHdr_gf256_h, kJitHdr_ec_device_cuh, kJitHdr_ec_kernel_cuh};
-    nvrtcProgram prog = nullptr;
-    const std::string expr_s = "mec::fused_rs_hh_kernel<mec::GfJit, true, " + std::to_string(align) + ", " + std::to_string(eb_t) +
-                               ", false, " + (rows3d ? "true" : "false") + ">";
-    const char* expr = expr_s.c_str();
-    if (api.create(&prog, src.c_str(), "mec_jit.cu", 4, bodies, names) == NVRTC_SUCCESS) {
-      api.add_name(prog, expr);
-      const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
-                            "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
-                            "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS), "-DMEC_PIPE2=" MEC_STR(MEC_PIPE2),
-                            "-DMEC_GF_DIV=" MEC_STR(MEC_GF_DIV), "-DMEC_GF_GROUP=" MEC_STR(MEC_GF_GROUP),
-                            "-DMEC_FUSED_STEP=" MEC_STR(MEC_FUSED_STEP)};
-      nvrtcResult rc = api.compile(prog, 11, opts);
-      if (rc == NVRTC_SUCCESS) {
-        size_t sz = 0;
-        const char* lname = nullptr;
-        if (api.cubin_size(prog, &sz) == NVRTC_SUCCESS && sz > 0 && api.lowered(prog, expr, &lname) == NVRTC_SUCCESS) {
-          std::vector<char> cubin(sz);
-          api.cubin(prog, cubin.data());
-          cudaLibrary_t lib = nullptr;
-          cudaKernel_t kern = nullptr;
-          if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
-              cudaLibraryGetKernel(&kern, lib, lname) == cudaSuccess)
-            result = reinterpret_cast<void*>(kern);
-          else
-            cudaGetLastError();
-        }
-      } else {
-        size_t ls = 0;
-        api.log_size(prog, &ls);
-        std::string log(ls, 0);
-        if (ls) api.log(prog, &log[0]);
-        set_last_error("NVRTC specialisation failed, using the runtime-matrix kernel: " + log.substr(0, 800));
-      }
-      api.destroy(&prog);
-    }
-    jit_compiles_++;
-    jit_seconds_ += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  JitGlobals& g = jit_globals();
+  std::unique_lock<std::mutex> lk(g.mu);
+  JitEntry* e = nullptr;
+  for (auto& c : g.cache)
+    if (c->key == key) { e = c.get(); break; }
+  if (!e) {
+    g.cache.emplace_back(new JitEntry);
+    e = g.cache.back().get();
+    e->key = key;
+    e->spec = JitSpec{device_, k, r, align, eb_t, rows3d, hash_out, std::vector<uint8_t>(coef, coef + static_cast<size_t>(k) * r)};
   }
-  g_jit_cache.emplace_back(key, result);  // failures are cached too: never retry, fall back to the generic kernel
-  return result;
+  if (e->state == kJitReady) return e->kernel;
+  if (e->state == kJitFailed) return nullptr;
+  if (mode == 1) {
+    if (e->state == kJitAbsent) {
+      e->state = kJitCompiling;
+      lk.unlock();
+      jit_run(g, e);
+      lk.lock();
+    } else {
+      g.cv_done.wait(lk, [&] { return e->state == kJitReady || e->state == kJitFailed; });
+    }
+    return e->state == kJitReady ? e->kernel : nullptr;
+  }
+  e->heat += in_bytes;
+  if (e->state == kJitAbsent && e->heat >= kJitHeatBytes) {
+    e->state = kJitCompiling;
+    g.queue.push_back(e);
+    if (!g.worker.joinable()) g.worker = std::thread(jit_worker_main);
+    g.cv_work.notify_one();
+  }
+  return nullptr;
 }
 
 Engine::Engine(int device) : device_(device) {}
@@ -374,10 +496,13 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   bool jitted = false;
   if (!se && use_tma && d.r >= 1 && !opt.force_dynamic) {
     const int64_t in_bytes = d.nblocks * static_cast<int64_t>(d.S) * d.k;
-    if (opt.jit == 1 || (opt.jit < 0 && in_bytes >= (256ll << 20))) {
+    if (opt.jit != 0) {
+      const int mode = opt.jit == 1 ? 1 : -1;
       void* jk = nullptr;
-      if (!d.contiguous && !any_misaligned) jk = jit_kernel(d.k, d.r, d.coef, 0, eb == kStaticEb ? kStaticEb : 0, false, d.hash_outputs);  // decode rows, aligned staging
-      else if (d.contiguous && d.hash_outputs && eb == kStaticEb) jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false, true);  // any (k, m) encode
+      if (!d.contiguous && !any_misaligned)  // decode rows, aligned staging
+        jk = jit_kernel(d.k, d.r, d.coef, 0, eb == kStaticEb ? kStaticEb : 0, false, d.hash_outputs, mode, in_bytes);
+      else if (d.contiguous && d.hash_outputs && eb == kStaticEb)  // any (k, m) encode
+        jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false, true, mode, in_bytes);
       if (jk) { kfn = jk; jitted = true; }
     }
   }
@@ -396,6 +521,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   MEC_CUDA_OK(cudaLaunchKernel(kfn, dim3(static_cast<unsigned>(grid)), dim3(static_cast<unsigned>(threads)), args, smem, st));
   MEC_CUDA_OK(cudaGetLastError());
   launches_++;
+  if (jitted) jit_launches_++;
   return MEC_OK;
 }
 

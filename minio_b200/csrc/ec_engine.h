@@ -67,8 +67,9 @@ class Engine {
   int launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStream_t st);
   int64_t launches() const { return launches_; }
   void count_launch() { launches_++; }
-  int64_t jit_compiles() const { return jit_compiles_; }
-  double jit_seconds() const { return jit_seconds_; }
+  int64_t jit_compiles() const;  // process-wide
+  int64_t jit_launches() const { return jit_launches_; }  // launches of this engine that ran a specialised kernel
+  double jit_seconds() const;
   int num_sms() const { return num_sms_; }
 
  private:
@@ -76,10 +77,9 @@ class Engine {
   int num_sms_ = 0;
   void* encode_tiled_ = nullptr;  // cuTensorMapEncodeTiled
   int64_t launches_ = 0;
+  int64_t jit_launches_ = 0;
   // run-time specialised kernels, keyed by (k, r, matrix bytes)
-  void* jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out);
-  int64_t jit_compiles_ = 0;
-  double jit_seconds_ = 0;
+  void* jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out, int mode, int64_t in_bytes);
 };
 
 // grow-only device / pinned buffers

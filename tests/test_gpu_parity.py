@@ -399,6 +399,32 @@ def test_heal_with_runtime_specialised_kernels(mb, oracle, k, m, stale):
         c.close()
 
 
+def test_background_specialisation(mb, oracle):
+    """Default policy (option jit = -1): the first calls of a new erasure pattern run the generic kernel while NVRTC works on
+    a background thread; once the pattern is compiled later calls use the specialised kernel.  Same bytes either way."""
+    import time
+    k, m, bs, size = 6, 3, MiB, 48 * MiB + 999  # a geometry no other test uses: nothing in the process-wide cache yet
+    data = rand(size, 99)
+    files, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    n = k + m
+    stale = [i in (1, 7) for i in range(n)]
+    c = mb.Codec(k, m, bs)
+    srcs = [None if stale[i] else files[i] for i in range(n)]
+    outs = c.heal(srcs, stale, size)  # 48 MiB of input >= the 32 MiB warm-up: queued for compilation, served by the generic kernel
+    assert c.stat("jit_launches") == 0
+    for i in (1, 7):
+        assert np.array_equal(outs[i], files[i])
+    # the compile queue is process-wide (other tests' patterns may be ahead of this one): poll with real calls
+    t0 = time.time()
+    while c.stat("jit_launches") == 0 and time.time() - t0 < 120:
+        time.sleep(0.2)
+        outs = c.heal(srcs, stale, size)
+    assert c.stat("jit_launches") >= 1, "the specialised kernel never took over"
+    for i in (1, 7):
+        assert np.array_equal(outs[i], files[i])
+    c.close()
+
+
 @pytest.mark.parametrize("algo", [1, 2, 4])  # SHA256, HighwayHash256 (whole-file), BLAKE2b512
 def test_whole_file_bitrot(mb, oracle, algo):
     """wholeBitrotWriter (cmd/bitrot-whole.go:35-45) + BitrotAlgorithm.New (cmd/bitrot.go:47-64) + bitrotVerify's whole-file
