@@ -194,6 +194,11 @@ def sha256_sweep(k, m, sizes, total_bytes):
 if __name__ == "__main__":
     MiB = 1 << 20
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "gen":   # generic (runtime-matrix) kernel numbers only
+        reconstruct_case("gen r=4", 12, 4, MiB, 3552, {0, 1, 2, 3}, 3, 0)
+        reconstruct_case("gen r=2", 12, 4, MiB, 3552, {0, 1}, 3, 0)
+        reconstruct_case("gen r=1", 12, 4, MiB, 3552, {3}, 3, 0)
+        sys.exit(0)
     if only == "jit":
         for _ in range(3):
             jit_encode_case(10, 4, MiB, 4096)
