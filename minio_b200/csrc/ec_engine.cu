@@ -430,17 +430,20 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       const int sm16 = static_cast<int>(d.S & 15);
       const int64_t row_stride = static_cast<int64_t>(d.S) & ~15ll;
       if (se && !opt.no_rows3d && eb == kStaticEb && sm16 == se->sm16 && d.in_block_len == d.in_block_stride) {
-        const int raw3 = raw_row_3d(d.k, sm16, eb);
-        if (row_stride >= raw3) {
+        const int rg = rows_per_request_3d(d.k, sm16, eb);  // shard rows per request (ec_kernel.cuh)
+        const int raw3 = raw_row_3d(d.k, sm16, eb, rg);
+        const int shift_max = group_shift_3d((d.k - 1) / rg, sm16, rg);
+        if (row_stride >= raw3 + shift_max) {
           CUtensorMap m3;
           if (make_map(encode_tiled_, &m3, d.in_base, static_cast<uint64_t>(row_stride / 4), static_cast<uint64_t>(d.nblocks), stride,
                        static_cast<uint32_t>(raw3 / 4), static_cast<uint32_t>(eb), static_cast<uint64_t>(d.k),
-                       static_cast<uint64_t>(row_stride), static_cast<uint32_t>(d.k)) == MEC_OK) {
+                       static_cast<uint64_t>(row_stride), static_cast<uint32_t>(rg)) == MEC_OK) {
             rows3d = true;
             maps.m[1] = m3;
-            p.tiles_3d = static_cast<int>((row_stride - raw3) / kTile) + 1;
+            p.tiles_3d = static_cast<int>((row_stride - raw3 - shift_max) / kTile) + 1;
             p.raw_pitch = raw3;
-            for (int t = 0; t < d.k; t++) p.in_c0[t] = static_cast<int32_t>(t * row_stride);
+            // per-row fallback boxes (last tiles) start where the row's 3-D request would: same leading bytes
+            for (int t = 0; t < d.k; t++) p.in_c0[t] = static_cast<int32_t>(t * row_stride + group_shift_3d(t / rg, sm16, rg));
           }
         }
       }

@@ -81,20 +81,34 @@ struct GfDynamic {
 __host__ __device__ constexpr uint32_t raw_group_bytes(int eb, int raw_pitch) { return (static_cast<uint32_t>(eb) * raw_pitch + 127u) & ~127u; }
 
 __host__ __device__ constexpr uint32_t fused_smem_bytes(int k, int r, int eb, int raw_pitch, bool dynamic_gf) {
-  uint32_t b = 128 + 128;  // alignment slack + barrier
+  uint32_t b = 0;  // the mbarrier lives in the padding of the first aligned row; the dynamic segment is declared 128-byte aligned
   b += static_cast<uint32_t>(k) * raw_group_bytes(eb, raw_pitch);
   b += static_cast<uint32_t>(k + (r > 0 ? r : 0)) * eb * kRowPitch;
   if (dynamic_gf) b += static_cast<uint32_t>(k) * ((r + kRChunk - 1) / kRChunk) * kRChunk * 8 * 4;
   return b;
 }
 
-// Row width of the raw tile in 3-D fetch mode: every shard row is fetched at the uniform stride S & ~15, so row t
-// carries t * (S mod 16) leading bytes; padded so that eb rows are a multiple of 128 bytes (TMA destinations).
-__host__ __device__ constexpr int raw_row_3d(int k, int sm16, int eb) {
-  int r = (kTile + (k - 1) * sm16 + 15) / 16 * 16;
-  while ((eb * r) % 128) r += 16;
+// 3-D fetch mode: the k shard rows of a tile arrive in ceil(k / RG) requests of RG consecutive rows x eb blocks.  Inside
+// the tensor map every row sits at the uniform stride S & ~15, so row t starts t * (S mod 16) bytes into "its" map row;
+// each request starts at the 16-byte boundary below its first row, which leaves row t with row_lead_3d() leading bytes.
+// RG is the largest group whose widest row still fits the 288-byte pitch of the aligned tile: one request for shards
+// that are 16-byte multiples, three for RS(12,4) at 1 MiB (S mod 16 = 6) — the narrow pitch is what lets a seventh CTA
+// fit on the SM.
+__host__ __device__ constexpr int group_shift_3d(int g, int sm16, int rg) { return (g * rg * sm16) & ~15; }
+__host__ __device__ constexpr int row_lead_3d(int t, int sm16, int rg) { return t * sm16 - group_shift_3d(t / rg, sm16, rg); }
+__host__ __device__ constexpr int raw_row_3d(int k, int sm16, int eb, int rg) {
+  int lead = 0;
+  for (int t = 0; t < k; t++) lead = row_lead_3d(t, sm16, rg) > lead ? row_lead_3d(t, sm16, rg) : lead;
+  int r = (kTile + lead + 15) / 16 * 16;
+  while ((rg * eb * r) % 128) r += 16;  // every request lands on a 128-byte boundary
   return r;
 }
+__host__ __device__ constexpr int rows_per_request_3d(int k, int sm16, int eb) {
+  for (int rg = k; rg > 1; rg--)
+    if (raw_row_3d(k, sm16, eb, rg) <= kRowPitch && (eb * raw_row_3d(k, sm16, eb, rg)) % 128 == 0) return rg;
+  return 1;
+}
+__host__ __device__ constexpr int raw_row_3d(int k, int sm16, int eb) { return raw_row_3d(k, sm16, eb, rows_per_request_3d(k, sm16, eb)); }
 
 #ifndef MEC_MIN_BLOCKS
 #define MEC_MIN_BLOCKS 3
@@ -159,8 +173,7 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   // MEC_PIPE2: software-pipelined loop (TMA lead of a whole tile).  Measured: removes the mbarrier wait stall but costs
   // ~3% more instructions; net -1.5% on RS(12,4) at full occupancy, so it is off by default.
   constexpr bool PIPE2 = MEC_PIPE2 && GF::kIsStatic && USE_TMA && !AUTO && (GF::K + GF::R) >= 16;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+  extern __shared__ __align__(128) uint8_t smem[];
   const int k = GF::kIsStatic ? GF::K : p.k;
   const int r = GF::kIsStatic ? GF::R : p.r;
   const int eb = EB_T > 0 ? EB_T : p.eb;
@@ -168,15 +181,18 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp_id = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const bool warp0 = warp_id == 0;
-  constexpr int kRaw3 = ROWS3D ? raw_row_3d(GF::K > 0 ? GF::K : 1, ALIGN > 0 ? ALIGN : 0, EB_T > 0 ? EB_T : 1) : kRawRow;
+  constexpr int kK3 = GF::K > 0 ? GF::K : 1, kSm3 = ALIGN > 0 ? ALIGN : 0, kEb3 = EB_T > 0 ? EB_T : 1;
+  constexpr int kRG = ROWS3D ? rows_per_request_3d(kK3, kSm3, kEb3) : 1;  // shard rows per 3-D request
+  constexpr int kRaw3 = ROWS3D ? raw_row_3d(kK3, kSm3, kEb3) : kRawRow;
   const uint32_t rawp = ROWS3D ? static_cast<uint32_t>(kRaw3) : (EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch));
   const uint32_t group_bytes = raw_group_bytes(eb, static_cast<int>(rawp));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-  uint32_t* s_arrive = reinterpret_cast<uint32_t*>(smem + 64);
-  uint8_t* s_raw = smem + 128;                                               // [k][group]
+  uint8_t* s_raw = smem;                                                     // [k][group]
   uint8_t* s_clean = s_raw + static_cast<uint32_t>(k) * group_bytes;         // [eb][k][kRowPitch]
   uint8_t* s_par = s_clean + static_cast<uint32_t>(k) * eb * kRowPitch;      // [eb][r][kRowPitch]
   uint32_t* s_masks = reinterpret_cast<uint32_t*>(s_par + static_cast<uint32_t>(r) * eb * kRowPitch);
+  // bytes [256, 288) of an aligned row are bank-skew padding nobody reads or writes: the mbarrier sits in row 0's
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_clean + kTile);
+  uint32_t* s_arrive = reinterpret_cast<uint32_t*>(s_clean + kTile + 16);
   const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
 
   const int32_t S = p.S;
@@ -238,10 +254,17 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
         const uint32_t bar = smem_u32(&bars[0]);
         const uint32_t dst0 = smem_u32(s_raw);
         if constexpr (ROWS3D) {
-          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRaw3);
-          if (i < p.tiles_3d) {  // one request for the whole tile
-            if (part == 0) tma_load_3d(dst0, &maps.m[1], i * (kTile / 4), static_cast<int32_t>(b0), 0, bar);
+          constexpr int kGroups = (kK3 + kRG - 1) / kRG;
+          if (i < p.tiles_3d) {  // kGroups requests for the whole tile (rows past k are out of bounds: zero fill, still counted)
+            if (part == 0) {
+              mbar_expect_tx(bar, static_cast<uint32_t>(kGroups * kRG) * eb * kRaw3);
+#pragma unroll
+              for (int gq = 0; gq < kGroups; gq++)
+                tma_load_3d(dst0 + static_cast<uint32_t>(gq * kRG) * group_bytes, &maps.m[1],
+                            i * (kTile / 4) + group_shift_3d(gq, kSm3, kRG) / 4, static_cast<int32_t>(b0), gq * kRG, bar);
+            }
           } else {               // last tiles of the shard: per-row boxes, zero padding via out-of-bounds fill
+            if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRaw3);
             for (int t = part; t < k; t += parts)
               tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
                           static_cast<int32_t>(b0), bar);
@@ -326,7 +349,7 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
             constexpr int t = decltype(t_)::value;
             uint2 v;
             if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
-            else v = load_col_ct<ROWS3D ? (t * ALIGN) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
+            else v = load_col_ct<ROWS3D ? row_lead_3d(t, kSm3, kRG) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
             lo[t] = v.x; hi[t] = v.y;
           });
         }
@@ -413,7 +436,7 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
             constexpr int t = decltype(t_)::value;
             uint2 v;
             if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
-            else v = load_col_ct<ROWS3D ? (t * ALIGN) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
+            else v = load_col_ct<ROWS3D ? row_lead_3d(t, kSm3, kRG) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
             lo[t] = v.x; hi[t] = v.y;
             *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
           });

@@ -13,7 +13,7 @@ except Exception as e: print("bench parse failed", e); print(open('gpurun_out/be
 PY
 for v in $EXTRA_ENVS; do echo "== bench $v"; env $v timeout 300 python bench.py --steps 3 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('GiB/s %.1f frac %.3f'%(d['value'],d['roofline']['frac']))"; done
 M=smsp__inst_executed.sum,sm__inst_executed.avg.per_cycle_elapsed,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active,sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active,smsp__warps_active.avg.per_cycle_active,smsp__warps_eligible.avg.per_cycle_active,gpu__time_duration.sum,launch__registers_per_thread,launch__occupancy_limit_shared_mem,launch__occupancy_limit_registers,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,smsp__average_warps_issue_stalled_wait_per_issue_active.ratio,smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio,smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio,smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio,smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio,smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio,smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio,sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active,sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active
-timeout 600 ncu --metrics $M --clock-control none -k regex:fused_rs_hh -s 3 -c 1 --csv --log-file $O/quick_ncu.csv python bench.py --blocks 3552 --steps 1 --warmup 3 --no-e2e --no-cpu > $O/quick_ncu.log 2>&1; echo "ncu rc=$?"
+timeout 600 ncu --metrics $M --clock-control none -k regex:fused_rs_hh -s 3 -c 1 --csv --log-file $O/quick_ncu.csv python bench.py --blocks 4144 --steps 1 --warmup 3 --no-e2e --no-cpu > $O/quick_ncu.log 2>&1; echo "ncu rc=$?"
 python - <<'PY'
 import csv
 try:
