@@ -107,6 +107,7 @@ extern "C" int mec_codec_new(int k, int m, int64_t block_size, int algo, int dev
   if (const char* e = getenv("MEC_FORCE_BYTEWISE")) c->opt.force_bytewise = atoi(e);
   if (const char* e = getenv("MEC_FORCE_DYNAMIC")) c->opt.force_dynamic = atoi(e);
   if (const char* e = getenv("MEC_GRID_MULT")) c->opt.grid_mult = atoi(e);
+  if (const char* e = getenv("MEC_BALANCE_GRID")) c->opt.balance_grid = atoi(e);
   if (const char* e = getenv("MEC_USE_AUTO")) c->opt.use_auto = atoi(e);
   if (const char* e = getenv("MEC_JIT")) c->opt.jit = atoi(e);
   if (const char* e = getenv("MEC_NO_ROWS3D")) c->opt.no_rows3d = atoi(e);
@@ -146,6 +147,7 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else if (!strcmp(name, "force_bytewise")) c->opt.force_bytewise = static_cast<int>(v);
   else if (!strcmp(name, "force_dynamic")) c->opt.force_dynamic = static_cast<int>(v);
   else if (!strcmp(name, "grid_mult")) c->opt.grid_mult = static_cast<int>(v);
+  else if (!strcmp(name, "balance_grid")) c->opt.balance_grid = static_cast<int>(v);
   else if (!strcmp(name, "use_auto")) c->opt.use_auto = static_cast<int>(v);
   else if (!strcmp(name, "jit")) c->opt.jit = static_cast<int>(v);
   else if (!strcmp(name, "no_rows3d")) c->opt.no_rows3d = static_cast<int>(v);

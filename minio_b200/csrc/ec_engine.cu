@@ -519,6 +519,10 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   const int64_t ngroups = (d.nblocks + eb - 1) / eb;
   int64_t grid = static_cast<int64_t>(per_sm) * num_sms_;
   if (grid > ngroups) grid = ngroups;
+  if (opt.balance_grid && grid > 0) {  // same number of passes for every CTA: no half-empty last wave
+    const int64_t passes = (ngroups + grid - 1) / grid;
+    grid = (ngroups + passes - 1) / passes;
+  }
 
   void* args[] = {&p, &maps};
   MEC_CUDA_OK(cudaLaunchKernel(kfn, dim3(static_cast<unsigned>(grid)), dim3(static_cast<unsigned>(threads)), args, smem, st));

@@ -51,6 +51,7 @@ struct EngineOptions {
   int eb = 0;              // erasure blocks per CTA (0 = auto)
   int force_bytewise = 0;  // 1: never use TMA
   int force_dynamic = 0;   // 1: never use the compile-time specialised GF kernels
+  int balance_grid = 0;  // shrink the persistent grid so that every CTA makes the same number of passes
   int grid_mult = 0;       // CTAs per SM (0 = occupancy)
   int jit = -1;            // decode-matrix kernels specialised at run time with NVRTC: -1 auto (large launches), 0 never, 1 always
   int no_rows3d = 0;       // 1: never use the one-request-per-tile 3-D TMA fetch
