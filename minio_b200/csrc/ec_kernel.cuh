@@ -158,7 +158,7 @@ __host__ __device__ constexpr int fused_max_threads() {
 }
 template <class GF, int ALIGN, int EB_T, bool ROWS3D>
 __host__ __device__ constexpr int fused_min_blocks() {
-  if (!GF::kIsStatic) return 2;  // runtime-matrix kernels keep 8 bit-plane accumulators per output row: 80 registers spill
+  if constexpr (!GF::kIsStatic) return GF::RC >= 2 ? 2 : MEC_MIN_BLOCKS;  // 8 bit-plane accumulators per output row: two or four rows spill at 80 registers
   if (!(EB_T > 0 && GF::K > 0)) return MEC_MIN_BLOCKS;
   constexpr int t = fused_max_threads<GF, EB_T>();
   const int by_regs = 65536 / (72 * t);

@@ -198,6 +198,7 @@ if __name__ == "__main__":
         reconstruct_case("gen r=4", 12, 4, MiB, 3552, {0, 1, 2, 3}, 3, 0)
         reconstruct_case("gen r=2", 12, 4, MiB, 3552, {0, 1}, 3, 0)
         reconstruct_case("gen r=1", 12, 4, MiB, 3552, {3}, 3, 0)
+        verify_case(12, 4, MiB, 10240, 9)
         sys.exit(0)
     if only == "jit":
         for _ in range(3):
