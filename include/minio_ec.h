@@ -182,6 +182,10 @@ int mec_set_option(mec_codec* c, const char* name, int64_t value);
  * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms" (both process-wide), "jit_launches".  -1 for unknown names.
  * Every ABI call is also wrapped in an NVTX range (visible in Nsight Systems) — the tracing hook of SURVEY §5. */
 int64_t mec_get_stat(const mec_codec* c, const char* name);
+/* Stops background kernel specialisation and waits for a compile in flight.  Call before the process exits (exit()
+ * during an NVRTC compile lets libnvrtc's exit handlers run under the compiling thread); later calls of the library
+ * keep working with the kernels already in the cache.  Also registered with atexit() after the first background compile. */
+void mec_shutdown(void);
 /* number of kernels launched by this codec so far (bench.py's gpu_launches) */
 int64_t mec_launch_count(const mec_codec* c);
 

@@ -62,6 +62,10 @@ def lib():
     L.mec_heal.argtypes = [vp, vp, i64, vp]
     L.mec_decode_prefer.restype = i64
     L.mec_decode_prefer.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
+    L.mec_shutdown.restype = None
+    L.mec_shutdown.argtypes = []
+    import atexit
+    atexit.register(L.mec_shutdown)  # no NVRTC compile may be in flight when the C runtime starts its exit handlers
     L.mec_get_stat.restype = i64
     L.mec_get_stat.argtypes = [vp, C.c_char_p]
     L.mec_bitrot_verify.argtypes = [vp, vp, i64, i64]

@@ -169,6 +169,8 @@ extern "C" int64_t mec_get_stat(const mec_codec* c, const char* name) {
   if (!strcmp(name, "jit_ms")) return c->eng ? static_cast<int64_t>(c->eng->jit_seconds() * 1e3) : 0;
   return -1;
 }
+extern "C" void mec_shutdown(void) { mec::jit_shutdown(); }
+
 extern "C" int64_t mec_launch_count(const mec_codec* c) { return (c && c->eng) ? c->eng->launches() : 0; }
 
 static int require_streaming(mec_codec* c) {

@@ -143,22 +143,28 @@ struct JitGlobals {
   std::condition_variable cv_done, cv_work;
   std::vector<std::unique_ptr<JitEntry>> cache;
   std::deque<JitEntry*> queue;
-  std::thread worker;
-  bool stop = false;
+  bool worker_started = false, worker_busy = false, stop = false, atexit_registered = false;
   int64_t compiles = 0;
   double seconds = 0;
-  ~JitGlobals() {
-    {
-      std::lock_guard<std::mutex> lk(mu);
-      stop = true;
-    }
-    cv_work.notify_all();
-    if (worker.joinable()) worker.join();
-  }
 };
+// Never destroyed: the worker thread is detached and must not outlive its mutex.  Process exit while the worker sits
+// idle on its condition variable is harmless; exit DURING a compile is not (libnvrtc's own exit handlers tear LLVM state
+// down under the compiling thread), hence mec_shutdown() — called by the host before it exits, and registered with
+// atexit() after the first compile as a best effort for hosts that do not.
 JitGlobals& jit_globals() {
-  static JitGlobals g;
-  return g;
+  static JitGlobals* g = new JitGlobals;
+  return *g;
+}
+
+void jit_quiesce() {
+  JitGlobals& g = jit_globals();
+  std::unique_lock<std::mutex> lk(g.mu);
+  g.stop = true;
+  for (JitEntry* e : g.queue) e->state = kJitAbsent;  // never started: a synchronous caller may still compile them
+  g.queue.clear();
+  g.cv_done.notify_all();
+  g.cv_work.notify_all();
+  g.cv_done.wait(lk, [&] { return !g.worker_busy; });
 }
 
 // NVRTC-instantiate the kernel template for one concrete matrix; returns a cudaKernel_t or nullptr
@@ -187,10 +193,10 @@ void* compile_specialised(const JitSpec& sp) {
   api.add_name(prog, expr);
   const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
                         "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
-                        "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS), "-DMEC_PIPE2=" MEC_STR(MEC_PIPE2),
+                        "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS),
                         "-DMEC_GF_DIV=" MEC_STR(MEC_GF_DIV), "-DMEC_GF_GROUP=" MEC_STR(MEC_GF_GROUP),
                         "-DMEC_FUSED_STEP=" MEC_STR(MEC_FUSED_STEP)};
-  nvrtcResult rc = api.compile(prog, 11, opts);
+  nvrtcResult rc = api.compile(prog, 10, opts);
   if (rc == NVRTC_SUCCESS) {
     size_t sz = 0;
     const char* lname = nullptr;
@@ -241,11 +247,23 @@ void jit_worker_main() {
       if (g.stop) return;
       e = g.queue.front();
       g.queue.pop_front();
+      g.worker_busy = true;
     }
     jit_run(g, e);
+    {
+      std::lock_guard<std::mutex> lk(g.mu);
+      g.worker_busy = false;
+      if (!g.atexit_registered) {  // registered late on purpose: runs before the handlers libnvrtc installed while compiling
+        g.atexit_registered = true;
+        atexit(jit_quiesce);
+      }
+    }
+    g.cv_done.notify_all();
   }
 }
 }  // namespace
+
+void jit_shutdown() { jit_quiesce(); }
 
 int64_t Engine::jit_compiles() const {
   JitGlobals& g = jit_globals();
@@ -279,21 +297,26 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t,
   if (e->state == kJitReady) return e->kernel;
   if (e->state == kJitFailed) return nullptr;
   if (mode == 1) {
-    if (e->state == kJitAbsent) {
-      e->state = kJitCompiling;
-      lk.unlock();
-      jit_run(g, e);
-      lk.lock();
-    } else {
-      g.cv_done.wait(lk, [&] { return e->state == kJitReady || e->state == kJitFailed; });
+    while (e->state != kJitReady && e->state != kJitFailed) {
+      if (e->state == kJitAbsent) {
+        e->state = kJitCompiling;
+        lk.unlock();
+        jit_run(g, e);
+        lk.lock();
+      } else {
+        g.cv_done.wait(lk);  // the background worker (or another caller) is on it
+      }
     }
     return e->state == kJitReady ? e->kernel : nullptr;
   }
   e->heat += in_bytes;
-  if (e->state == kJitAbsent && e->heat >= kJitHeatBytes) {
+  if (e->state == kJitAbsent && e->heat >= kJitHeatBytes && !g.stop) {
     e->state = kJitCompiling;
     g.queue.push_back(e);
-    if (!g.worker.joinable()) g.worker = std::thread(jit_worker_main);
+    if (!g.worker_started) {
+      g.worker_started = true;
+      std::thread(jit_worker_main).detach();
+    }
     g.cv_work.notify_one();
   }
   return nullptr;
@@ -406,7 +429,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   // fetched from the aligned-down address and the kernel skips in_align[t] bytes.
   const int64_t ntiles = (static_cast<int64_t>(d.S) + kTile - 1) / kTile;
   bool use_tma = !opt.force_bytewise && d.S > 0;
-  bool any_misaligned = false, rows3d = false;
+  bool any_misaligned = false, rows3d = false, direct = false;
   p.in_block_stride = d.in_block_stride;
   p.raw_pitch = kRawRow;
   if (d.contiguous) {
@@ -423,15 +446,18 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       p.in_align[t] = static_cast<uint8_t>(off & 15);
       any_misaligned |= (off & 15) != 0;
     }
+    // every row 16-byte aligned and a kernel instantiated for ALIGN == 0: TMA writes the hash threads' rows directly
+    direct = use_tma && !any_misaligned && !(opt.use_auto && se && se->aligned_auto) && (!se || eb == kStaticEb);
     if (use_tma) {
       p.tma_mode = kLoadTmaBlocks2D;
       const uint64_t stride = d.nblocks > 1 ? static_cast<uint64_t>(d.in_block_stride) : static_cast<uint64_t>(d.in_block_len);
       // 3-D fetch mode (compile-time specialised encode only): rows at the uniform stride S & ~15
       const int sm16 = static_cast<int>(d.S & 15);
       const int64_t row_stride = static_cast<int64_t>(d.S) & ~15ll;
-      if (se && !opt.no_rows3d && eb == kStaticEb && sm16 == se->sm16 && d.in_block_len == d.in_block_stride) {
-        const int rg = rows_per_request_3d(d.k, sm16, eb);  // shard rows per request (ec_kernel.cuh)
-        const int raw3 = raw_row_3d(d.k, sm16, eb, rg);
+      if (se && !opt.no_rows3d && eb == kStaticEb && sm16 == se->sm16 && d.in_block_len == d.in_block_stride &&
+          !(opt.use_auto && se->aligned_auto && sm16 == 0)) {
+        const int rg = direct ? d.k : rows_per_request_3d(d.k, sm16, eb);  // shard rows per request (ec_kernel.cuh)
+        const int raw3 = direct ? kRowPitch : raw_row_3d(d.k, sm16, eb, rg);
         const int shift_max = group_shift_3d((d.k - 1) / rg, sm16, rg);
         if (row_stride >= raw3 + shift_max) {
           CUtensorMap m3;
@@ -448,7 +474,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
         }
       }
       int rc = make_map(encode_tiled_, &maps.m[0], d.in_base, static_cast<uint64_t>(d.in_block_len / 4),
-                        static_cast<uint64_t>(d.nblocks), stride, static_cast<uint32_t>((rows3d ? p.raw_pitch : kRawRow) / 4),
+                        static_cast<uint64_t>(d.nblocks), stride, static_cast<uint32_t>((rows3d ? p.raw_pitch : (direct ? kRowPitch : kRawRow)) / 4),
                         static_cast<uint32_t>(eb));
       if (rc) return rc;
     }
@@ -471,17 +497,19 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
         any_misaligned |= (off & 15) != 0;
       }
     }
+    direct = use_tma && !any_misaligned;  // runtime-matrix and NVRTC kernels for aligned rows are ALIGN == 0 instantiations
     if (use_tma) {
       p.tma_mode = kLoadTmaPerInput;
       for (int t = 0; t < d.k; t++) {
         int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], static_cast<uint64_t>(row_bytes / 4), static_cast<uint64_t>(d.nblocks),
-                          static_cast<uint64_t>(row_bytes), kRawRow / 4, static_cast<uint32_t>(eb));
+                          static_cast<uint64_t>(row_bytes), (direct ? kRowPitch : kRawRow) / 4, static_cast<uint32_t>(eb));
         if (rc) return rc;
       }
     }
   }
   if (!use_tma) p.tma_mode = kLoadBytewise;
   if (!use_tma) p.raw_pitch = kRawRow;
+  else if (direct) p.raw_pitch = kRowPitch;
 
   KernelFn fn;
   if (se) {
@@ -509,7 +537,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       if (jk) { kfn = jk; jitted = true; }
     }
   }
-  const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr && !jitted);
+  const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr && !jitted, direct);
   if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;
   MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   int per_sm = 0;

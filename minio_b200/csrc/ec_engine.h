@@ -83,6 +83,9 @@ class Engine {
   void* jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out, int mode, int64_t in_bytes);
 };
 
+// stop background specialisation and wait for a compile in flight (mec_shutdown)
+void jit_shutdown();
+
 // grow-only device / pinned buffers
 struct DevBuf {
   void* p = nullptr;

@@ -80,13 +80,21 @@ struct GfDynamic {
 
 __host__ __device__ constexpr uint32_t raw_group_bytes(int eb, int raw_pitch) { return (static_cast<uint32_t>(eb) * raw_pitch + 127u) & ~127u; }
 
-__host__ __device__ constexpr uint32_t fused_smem_bytes(int k, int r, int eb, int raw_pitch, bool dynamic_gf) {
-  uint32_t b = 0;  // the mbarrier lives in the padding of the first aligned row; the dynamic segment is declared 128-byte aligned
-  b += static_cast<uint32_t>(k) * raw_group_bytes(eb, raw_pitch);
-  b += static_cast<uint32_t>(k + (r > 0 ? r : 0)) * eb * kRowPitch;
+// `direct`: every input row is 16-byte aligned, TMA writes straight into the 288-byte-pitch rows the hash threads read —
+// two such buffers (tile i is hashed while tile i+1 lands), no re-aligned copy.  Otherwise: one raw tile + one aligned tile.
+__host__ __device__ constexpr uint32_t fused_smem_bytes(int k, int r, int eb, int raw_pitch, bool dynamic_gf, bool direct = false) {
+  uint32_t b = 0;  // the mbarriers live in row padding; the dynamic segment is declared 128-byte aligned
+  if (direct) {
+    b += static_cast<uint32_t>(2 * k + (r > 0 ? r : 0)) * raw_group_bytes(eb, kRowPitch);
+    if (r <= 0) b += 128;  // no output rows to hide the barriers in
+  } else {
+    b += static_cast<uint32_t>(k) * raw_group_bytes(eb, raw_pitch);
+    b += static_cast<uint32_t>(k + (r > 0 ? r : 0)) * eb * kRowPitch;
+  }
   if (dynamic_gf) b += static_cast<uint32_t>(k) * ((r + kRChunk - 1) / kRChunk) * kRChunk * 8 * 4;
   return b;
 }
+__host__ __device__ constexpr bool fused_is_direct(bool use_tma, int align, bool autop) { return use_tma && align == 0 && !autop; }
 
 // 3-D fetch mode: the k shard rows of a tile arrive in ceil(k / RG) requests of RG consecutive rows x eb blocks.  Inside
 // the tensor map every row sits at the uniform stride S & ~15, so row t starts t * (S mod 16) bytes into "its" map row;
@@ -112,9 +120,6 @@ __host__ __device__ constexpr int raw_row_3d(int k, int sm16, int eb) { return r
 
 #ifndef MEC_MIN_BLOCKS
 #define MEC_MIN_BLOCKS 3
-#endif
-#ifndef MEC_PIPE2
-#define MEC_PIPE2 0
 #endif
 
 // one 8-byte column of raw row `row` whose logical byte 0 sits `A` bytes into the row
@@ -156,23 +161,20 @@ template <class GF, int EB_T>
 __host__ __device__ constexpr int fused_max_threads() {
   return (EB_T > 0 && GF::K > 0) ? ((2 * (GF::K + GF::R) * EB_T + 31) / 32 * 32) : 256;
 }
-template <class GF, int ALIGN, int EB_T, bool ROWS3D>
+template <class GF, int ALIGN, int EB_T, bool ROWS3D, bool DIRECT>
 __host__ __device__ constexpr int fused_min_blocks() {
   if constexpr (!GF::kIsStatic) return GF::RC >= 2 ? 2 : MEC_MIN_BLOCKS;  // 8 bit-plane accumulators per output row: two or four rows spill at 80 registers
   if (!(EB_T > 0 && GF::K > 0)) return MEC_MIN_BLOCKS;
   constexpr int t = fused_max_threads<GF, EB_T>();
   const int by_regs = 65536 / (72 * t);
   const int raw = ROWS3D ? raw_row_3d(GF::K > 0 ? GF::K : 1, ALIGN > 0 ? ALIGN : 0, EB_T > 0 ? EB_T : 1) : kRawRow;
-  const int by_smem = 233472 / (static_cast<int>(fused_smem_bytes(GF::K, GF::R, EB_T, raw, false)) + 1024);
+  const int by_smem = 233472 / (static_cast<int>(fused_smem_bytes(GF::K, GF::R, EB_T, raw, false, DIRECT)) + 1024);
   const int b = by_regs < by_smem ? by_regs : by_smem;
   return b > 0 ? b : 1;
 }
 template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO, bool ROWS3D = false>
-__global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_blocks<GF, ALIGN, EB_T, ROWS3D>())) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
+__global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_blocks<GF, ALIGN, EB_T, ROWS3D, fused_is_direct(USE_TMA, ALIGN, AUTO)>())) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
-  // MEC_PIPE2: software-pipelined loop (TMA lead of a whole tile).  Measured: removes the mbarrier wait stall but costs
-  // ~3% more instructions; net -1.5% on RS(12,4) at full occupancy, so it is off by default.
-  constexpr bool PIPE2 = MEC_PIPE2 && GF::kIsStatic && USE_TMA && !AUTO && (GF::K + GF::R) >= 16;
   extern __shared__ __align__(128) uint8_t smem[];
   const int k = GF::kIsStatic ? GF::K : p.k;
   const int r = GF::kIsStatic ? GF::R : p.r;
@@ -181,18 +183,26 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp_id = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const bool warp0 = warp_id == 0;
+  constexpr bool DIRECT = fused_is_direct(USE_TMA, ALIGN, AUTO);
   constexpr int kK3 = GF::K > 0 ? GF::K : 1, kSm3 = ALIGN > 0 ? ALIGN : 0, kEb3 = EB_T > 0 ? EB_T : 1;
-  constexpr int kRG = ROWS3D ? rows_per_request_3d(kK3, kSm3, kEb3) : 1;  // shard rows per 3-D request
-  constexpr int kRaw3 = ROWS3D ? raw_row_3d(kK3, kSm3, kEb3) : kRawRow;
-  const uint32_t rawp = ROWS3D ? static_cast<uint32_t>(kRaw3) : (EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch));
+  constexpr int kRG = ROWS3D ? (DIRECT ? kK3 : rows_per_request_3d(kK3, kSm3, kEb3)) : 1;  // shard rows per 3-D request
+  constexpr int kRaw3 = ROWS3D ? (DIRECT ? kRowPitch : raw_row_3d(kK3, kSm3, kEb3)) : kRawRow;
+  const uint32_t rawp = DIRECT ? static_cast<uint32_t>(kRowPitch)
+                               : (ROWS3D ? static_cast<uint32_t>(kRaw3) : (EB_T > 0 ? static_cast<uint32_t>(kRawRow) : static_cast<uint32_t>(p.raw_pitch)));
   const uint32_t group_bytes = raw_group_bytes(eb, static_cast<int>(rawp));
-  uint8_t* s_raw = smem;                                                     // [k][group]
-  uint8_t* s_clean = s_raw + static_cast<uint32_t>(k) * group_bytes;         // [eb][k][kRowPitch]
-  uint8_t* s_par = s_clean + static_cast<uint32_t>(k) * eb * kRowPitch;      // [eb][r][kRowPitch]
-  uint32_t* s_masks = reinterpret_cast<uint32_t*>(s_par + static_cast<uint32_t>(r) * eb * kRowPitch);
-  // bytes [256, 288) of an aligned row are bank-skew padding nobody reads or writes: the mbarrier sits in row 0's
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_clean + kTile);
-  uint32_t* s_arrive = reinterpret_cast<uint32_t*>(s_clean + kTile + 16);
+  const uint32_t buf_bytes = static_cast<uint32_t>(k) * group_bytes;
+  uint8_t* s_raw = smem;                                                     // [k][group]  (DIRECT: two of them)
+  uint8_t* s_clean = DIRECT ? s_raw : s_raw + buf_bytes;                     // [eb][k][kRowPitch]  (not DIRECT)
+  uint8_t* s_par = DIRECT ? s_raw + 2 * buf_bytes : s_clean + static_cast<uint32_t>(k) * eb * kRowPitch;
+  // output rows: [eb][r][kRowPitch], DIRECT: [r][group] like the inputs
+  const uint32_t par_row = DIRECT ? group_bytes : static_cast<uint32_t>(kRowPitch);
+  const uint32_t par_blk = DIRECT ? static_cast<uint32_t>(kRowPitch) : static_cast<uint32_t>(r) * kRowPitch;
+  uint32_t* s_masks = reinterpret_cast<uint32_t*>(s_par + (DIRECT ? static_cast<uint32_t>(r) * group_bytes + (r > 0 ? 0u : 128u)
+                                                                   : static_cast<uint32_t>(r) * eb * kRowPitch));
+  // bytes [256, 288) of an aligned / output row are bank-skew padding nobody reads or writes: the mbarriers sit in row 0's
+  // (DIRECT input rows are written by TMA over their full pitch, so there it is the first output row, or 128 spare bytes)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(DIRECT ? (r > 0 ? s_par + kTile : s_par) : s_clean + kTile);
+  uint32_t* s_arrive = reinterpret_cast<uint32_t*>(bars + 2);
   const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
 
   const int32_t S = p.S;
@@ -202,6 +212,7 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   if constexpr (USE_TMA) {
     if (tid == 0) {
       mbar_init(smem_u32(&bars[0]), 1);
+      if constexpr (DIRECT) mbar_init(smem_u32(&bars[1]), 1);
       fence_barrier_init();
       *s_arrive = 0;
     }
@@ -224,12 +235,16 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   const int nhash = (AUTO || GF::kHashOut == 1) ? nstreams : (GF::kHashOut == 0 ? k : p.nhash);
   const bool hh_thread = p.digests != nullptr && tid < 2 * nhash * eb;
   const int sl = tid >> 1, h = tid & 1;
-  const int e_hh = hh_thread ? sl / nhash : 0;
-  const int srow = hh_thread ? sl % nhash : 0;
+  // DIRECT rows are laid out [stream][block]: the four streams of a quarter-warp are then four blocks of one shard,
+  // 288 bytes apart — the same bank skew the aligned tile gets from its row pitch
+  const int e_hh = hh_thread ? (DIRECT ? sl % eb : sl / nhash) : 0;
+  const int srow = hh_thread ? (DIRECT ? sl / eb : sl % nhash) : 0;
   const bool is_out = srow >= k;
-  const uint8_t* hh_row = is_out ? s_par + static_cast<uint32_t>(e_hh * r + (srow - k)) * kRowPitch
-                                 : s_clean + static_cast<uint32_t>(e_hh * k + srow) * kRowPitch;
+  const uint8_t* hh_row = is_out ? s_par + static_cast<uint32_t>(srow - k) * par_row + static_cast<uint32_t>(e_hh) * par_blk
+                                 : (DIRECT ? s_raw + static_cast<uint32_t>(srow) * group_bytes + static_cast<uint32_t>(e_hh) * kRowPitch
+                                           : s_clean + static_cast<uint32_t>(e_hh * k + srow) * kRowPitch);
   const uint32_t hh_addr = smem_u32(hh_row) + 16u * h;
+  const uint32_t hh_flip = (DIRECT && !is_out) ? buf_bytes : 0u;  // added when the tile sits in the second buffer
 
   // ---- GF thread identity: one 8-byte column (threads beyond eb*32 columns idle in the GF step)
   const int ncol = eb * (kTile / 8);
@@ -251,8 +266,9 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
     // arriving before expect_tx is legal, the phase cannot complete before the arrival).  Byte-wise: all threads.
     auto issue_tile_at = [&](int i, int64_t b0, int nb, int part, int parts) {
       if constexpr (USE_TMA) {
-        const uint32_t bar = smem_u32(&bars[0]);
-        const uint32_t dst0 = smem_u32(s_raw);
+        const uint32_t sel = DIRECT ? ((it + static_cast<uint32_t>(i)) & 1u) : 0u;  // DIRECT: tiles alternate between two buffers
+        const uint32_t bar = smem_u32(&bars[sel]);
+        const uint32_t dst0 = smem_u32(s_raw) + sel * buf_bytes;
         if constexpr (ROWS3D) {
           constexpr int kGroups = (kK3 + kRG - 1) / kRG;
           if (i < p.tiles_3d) {  // kGroups requests for the whole tile (rows past k are out of bounds: zero fill, still counted)
@@ -270,12 +286,12 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
                           static_cast<int32_t>(b0), bar);
           }
         } else if (p.tma_mode == kLoadTmaBlocks2D) {
-          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
+          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * rawp);
           for (int t = part; t < k; t += parts)
             tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
                         static_cast<int32_t>(b0), bar);
         } else {  // one map per input stream: rows = erasure blocks of that stream, box {272 B, eb blocks}
-          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRawRow);
+          if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * rawp);
           for (int t = part; t < k; t += parts)
             tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[t], (p.in_c0[t] + i * kTile) >> 2,
                         static_cast<int32_t>(b0), bar);
@@ -298,7 +314,12 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
     if constexpr (USE_TMA) {
       // AUTO: later groups are pre-issued by the last arriver of the previous group's final tile
       if (warp0 && (!AUTO || g == static_cast<int64_t>(blockIdx.x))) {
-        if (elect_one() && ntiles > 0) issue_tile(0);
+        if (elect_one() && ntiles > 0) {
+          issue_tile(0);
+          if constexpr (DIRECT) {
+            if (ntiles > 1) issue_tile(1);
+          }
+        }
         __syncwarp();
       }
     } else {
@@ -309,89 +330,34 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
     // ---- HH step: packets [8j, 8j+8) of every stream, from the aligned + output tiles
     auto hh_step = [&](int j) {
       if (hh_live) {
+        const uint32_t flip = (DIRECT && ((it + static_cast<uint32_t>(j)) & 1u)) ? hh_flip : 0u;
+        const uint32_t addr = hh_addr + flip;
         const int q0 = 8 * j;
         if (q0 + 8 <= npk) {
 #pragma unroll
           for (int q = 0; q < 8; q++) {
-            const uint4 v = lds128(hh_addr + 32 * q);
+            const uint4 v = lds128(addr + 32 * q);
             hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
           }
         } else {
 #pragma unroll 1
           for (int q = 0; q0 + q < npk; q++) {
-            const uint4 v = lds128(hh_addr + 32 * q);
+            const uint4 v = lds128(addr + 32 * q);
             hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
           }
         }
         if (j == ntiles - 1 && rem) {
-          const uint8_t* tail = hh_row + ((npk * 32) & (kTile - 1));
+          const uint8_t* tail = hh_row + flip + ((npk * 32) & (kTile - 1));
           hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
         }
       }
     };
 
-    // ---------------- software-pipelined tile loop (one column per thread, compile-time matrix):
-    //   wait raw(i) -> columns to registers -> barrier -> TMA(i+1) -> HH(i-1) -> barrier -> aligned tile + GF math
-    // The next raw tile is in flight during a whole hash step AND a whole GF step; still two barriers per tile.
-    if constexpr (PIPE2) {
-      constexpr int K = GF::K, R = GF::R;
-      const int c = tid;
-      const bool colv = c < ncol;
-      const int e = colv ? (c >> 5) : 0, x8 = c & 31;
-      const uint8_t* rcol = s_raw + e * rawp + x8 * 8;
-      uint8_t* crow = s_clean + static_cast<uint32_t>(e * k) * kRowPitch + x8 * 8;
-      uint8_t* prow = s_par + static_cast<uint32_t>(e * r) * kRowPitch + x8 * 8;
-      for (int i = 0; i < ntiles; i++) {
-        mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
-        uint32_t lo[K], hi[K];
-        if (colv) {
-          static_for<K>([&](auto t_) {
-            constexpr int t = decltype(t_)::value;
-            uint2 v;
-            if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
-            else v = load_col_ct<ROWS3D ? row_lead_3d(t, kSm3, kRG) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
-            lo[t] = v.x; hi[t] = v.y;
-          });
-        }
-        __syncthreads();  // (A) raw tile consumed; aligned + output tiles of tile i-1 complete
-        if (i + 1 < ntiles) {
-          if (elect_one()) issue_tile_at(i + 1, b0, nb, warp_id, nthr >> 5);
-          __syncwarp();
-        }
-        if (i > 0) hh_step(i - 1);
-        __syncthreads();  // (B) aligned + output tiles may be overwritten
-        if (colv) {
-          const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
-          uint8_t* gout = p.out + (b0 + e) * r * p.out_pitch + xg;
-          const bool full = e < nb && xg + 8 <= S;
-          const bool part = e < nb && xg < S && !full;
-#pragma unroll
-          for (int t = 0; t < K; t++) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = make_uint2(lo[t], hi[t]);
-          if constexpr (R > 0) {
-            uint32_t olo[R], ohi[R];
-            GfStaticApply<typename GF::Mat>::run(lo, olo);
-            GfStaticApply<typename GF::Mat>::run(hi, ohi);
-#pragma unroll
-            for (int j = 0; j < R; j++) {
-              const uint2 o = make_uint2(olo[j], ohi[j]);
-              *reinterpret_cast<uint2*>(prow + j * kRowPitch) = o;
-              uint8_t* gp = gout + j * p.out_pitch;
-              if (full) {
-                *reinterpret_cast<uint2*>(gp) = o;
-              } else if (part) {
-                const uint64_t w = pack64(o.x, o.y);
-                for (int q = 0; q < 8 && xg + q < S; q++) gp[q] = static_cast<uint8_t>(w >> (8 * q));
-              }
-            }
-          }
-        }
-      }
-      __syncthreads();  // aligned + output tiles of the last tile complete
-      if (ntiles > 0) hh_step(ntiles - 1);
-    } else {
     // ---------------- main tile loop (general form)
     for (int i = 0; i < ntiles; i++) {
-      if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
+      const uint32_t sel = DIRECT ? ((it + static_cast<uint32_t>(i)) & 1u) : 0u;
+      if constexpr (DIRECT) mbar_wait(smem_u32(&bars[sel]), ((it + static_cast<uint32_t>(i)) >> 1) & 1u);
+      else if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
 
       // ---- GF step on tile i: re-align, re-store, multiply, store
       auto raw_consumed = [&]() {  // AUTO: count this warp's arrival; the last arriver refills the raw tile
@@ -412,15 +378,15 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
       };
       for (int c = tid; c < ncol; c += nthr) {
         const int e = c >> 5, x8 = c & 31;
-        const uint8_t* rcol = s_raw + e * rawp + x8 * 8;
+        const uint8_t* rcol = s_raw + sel * buf_bytes + e * rawp + x8 * 8;
         uint8_t* crow = s_clean + static_cast<uint32_t>(e * k) * kRowPitch + x8 * 8;
-        uint8_t* prow = s_par + static_cast<uint32_t>(e * r) * kRowPitch + x8 * 8;
+        uint8_t* prow = s_par + static_cast<uint32_t>(e) * par_blk + x8 * 8;
         const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
         uint8_t* gout = p.out + (b0 + e) * r * p.out_pitch + xg;
         const bool full = e < nb && xg + 8 <= S;
         const bool part = e < nb && xg < S && !full;
         auto store_out = [&](int j, uint2 o) {
-          *reinterpret_cast<uint2*>(prow + j * kRowPitch) = o;
+          *reinterpret_cast<uint2*>(prow + static_cast<uint32_t>(j) * par_row) = o;
           uint8_t* gp = gout + j * p.out_pitch;
           if (full) {
             *reinterpret_cast<uint2*>(gp) = o;
@@ -438,7 +404,7 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
             if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
             else v = load_col_ct<ROWS3D ? row_lead_3d(t, kSm3, kRG) : ((t * ALIGN) & 15)>(rcol + t * group_bytes);
             lo[t] = v.x; hi[t] = v.y;
-            *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
+            if constexpr (!DIRECT) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
           });
           if constexpr (AUTO && USE_TMA) {
             // the raw tile is dead as soon as every lane holds its column in registers: signal it
@@ -466,7 +432,7 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
               uint2 v;
               if constexpr (ALIGN == kAlignRuntime) v = load_col_rt(rcol + t * group_bytes, p.in_align[t]);
               else v = *reinterpret_cast<const uint2*>(rcol + t * group_bytes);
-              if (j0 == 0) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
+              if constexpr (!DIRECT) { if (j0 == 0) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v; }
               if (r == 0) continue;
               const uint4* mk = reinterpret_cast<const uint4*>(s_masks + (t * rpad + j0) * 8);
 #pragma unroll
@@ -504,6 +470,23 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
           }
         }
       }
+      if constexpr (DIRECT) {
+        if (r > 0) __syncthreads();  // (A) output rows complete
+        hh_step(i);
+        __syncthreads();             // (B) everyone is done with this buffer (and the output rows): refill it two tiles ahead
+        if (i + 2 < ntiles) {
+          if constexpr (ROWS3D) {
+            if (warp0) {
+              if (elect_one()) issue_tile_at(i + 2, b0, nb, 0, 1);
+              __syncwarp();
+            }
+          } else {
+            if (elect_one()) issue_tile_at(i + 2, b0, nb, warp_id, nthr >> 5);
+            __syncwarp();
+          }
+        }
+        continue;
+      }
       if constexpr (AUTO && USE_TMA) {
         __syncwarp();  // (A) this warp's aligned + output rows are complete
         if constexpr (!GF::kIsStatic) raw_consumed();
@@ -528,8 +511,6 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
       if constexpr (AUTO && USE_TMA) __syncwarp();  // (B) this warp's rows may be overwritten
       else __syncthreads();                          // (B) aligned + output tiles may be overwritten
     }
-
-    }  // !PIPE2
 
     // ---------------- finalisation
     {

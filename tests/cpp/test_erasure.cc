@@ -323,7 +323,21 @@ static void TestBitrot() {
   CHECK(e->BitrotVerify(disk.data.data(), static_cast<int64_t>(disk.data.size()), 35) == Err::errFileCorrupt, "bitrotVerify corrupt");
 }
 
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+static void on_segv(int sig) {  // a backtrace instead of a silent exit code when something dies during teardown
+  void* frames[64];
+  const int n = backtrace(frames, 64);
+  const char msg[] = "fatal signal, backtrace:\n";
+  (void)!write(2, msg, sizeof(msg) - 1);
+  backtrace_symbols_fd(frames, n, 2);
+  _exit(128 + sig);
+}
+
 int main(int argc, char** argv) {
+  signal(SIGSEGV, on_segv);
+  signal(SIGABRT, on_segv);
   std::string only = argc > 1 ? argv[1] : "";
   if (mec_device_count() < 1) { fprintf(stderr, "no CUDA device\n"); return 3; }
   struct { const char* name; void (*fn)(); } all[] = {{"TestErasureEncodeDecode", TestErasureEncodeDecode}, {"TestErasureEncode", TestErasureEncode},
@@ -335,5 +349,6 @@ int main(int argc, char** argv) {
     t.fn();
     printf("%s %s\n", g_fail == before ? "ok  " : "FAIL", t.name);
   }
+  mec_shutdown();  // background specialisation must be idle before exit()
   return g_fail ? 1 : 0;
 }
