@@ -6,7 +6,7 @@ import sys, numpy as np
 sys.path.insert(0, '.'); sys.path.insert(0, 'tests')
 import minio_b200 as mb, oracle_lib as o
 rng = np.random.default_rng(3)
-for (k, m, bs, n) in [(12, 4, 1 << 20, (1 << 20) + 4321), (4, 2, 65536, 3 * 65536 + 17), (7, 5, 1 << 20, 600000)]:
+for (k, m, bs, n) in [(12, 4, 1 << 20, (1 << 20) + 4321), (8, 4, 1 << 20, 2 * (1 << 20) + 999), (4, 2, 65536, 3 * 65536 + 17), (7, 5, 1 << 20, 600000)]:
     data = rng.integers(0, 256, n, dtype=np.uint8)
     c = mb.Codec(k, m, bs)
     files = c.encode(data)
