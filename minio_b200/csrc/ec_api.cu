@@ -108,6 +108,7 @@ extern "C" int mec_codec_new(int k, int m, int64_t block_size, int algo, int dev
   if (const char* e = getenv("MEC_FORCE_DYNAMIC")) c->opt.force_dynamic = atoi(e);
   if (const char* e = getenv("MEC_GRID_MULT")) c->opt.grid_mult = atoi(e);
   if (const char* e = getenv("MEC_BALANCE_GRID")) c->opt.balance_grid = atoi(e);
+  if (const char* e = getenv("MEC_CHUNK_BLOCKS")) c->opt.chunk_blocks = atoll(e);
   if (const char* e = getenv("MEC_USE_AUTO")) c->opt.use_auto = atoi(e);
   if (const char* e = getenv("MEC_JIT")) c->opt.jit = atoi(e);
   if (const char* e = getenv("MEC_NO_ROWS3D")) c->opt.no_rows3d = atoi(e);
