@@ -118,6 +118,15 @@ __host__ __device__ constexpr int rows_per_request_3d(int k, int sm16, int eb) {
 }
 __host__ __device__ constexpr int raw_row_3d(int k, int sm16, int eb) { return raw_row_3d(k, sm16, eb, rows_per_request_3d(k, sm16, eb)); }
 
+// RS(12,4) at 1 MiB blocks (S mod 16 = 6): three requests of four rows at a 288-byte pitch, 32 256 bytes per CTA — seven
+// CTAs (7 x (32 256 + 1 024 reserved) <= 233 472) and 28 warps x 32 lanes x 72 registers = the whole register file.
+static_assert(rows_per_request_3d(12, 6, 4) == 4 && raw_row_3d(12, 6, 4) == kRowPitch, "RS(12,4) row groups");
+static_assert(row_lead_3d(7, 6, 4) == 26 && row_lead_3d(8, 6, 4) == 0 && group_shift_3d(2, 6, 4) == 48, "row leads");
+static_assert(fused_smem_bytes(12, 4, 4, raw_row_3d(12, 6, 4), false) == 32256, "RS(12,4) CTA footprint");
+static_assert(7 * (fused_smem_bytes(12, 4, 4, raw_row_3d(12, 6, 4), false) + 1024) <= 233472, "seven CTAs per SM");
+static_assert(fused_smem_bytes(12, 4, 4, kRowPitch, false, true) == 32256, "direct-fetch footprint equals raw + aligned");
+static_assert(rows_per_request_3d(8, 0, 4) == 8 && raw_row_3d(8, 0, 4) == kTile, "aligned shards: one request, no padding");
+
 #ifndef MEC_MIN_BLOCKS
 #define MEC_MIN_BLOCKS 3
 #endif

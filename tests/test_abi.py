@@ -94,3 +94,13 @@ def test_no_cpu_fallback(mb):
     syms = subprocess.check_output(["nm", "-D", mb.lib_path()], text=True)
     assert "orc_" not in syms
     c.close()
+
+
+def test_shutdown_is_callable_without_a_device():
+    """mec_shutdown only quiesces the background compiler: safe to call with no GPU, twice, before anything else ran."""
+    import minio_b200.capi as capi
+    L = capi.lib()
+    if L.mec_device_count() > 0:
+        pytest.skip("would switch background specialisation off for the GPU tests that share this process")
+    L.mec_shutdown()
+    L.mec_shutdown()
