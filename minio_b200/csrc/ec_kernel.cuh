@@ -7,19 +7,23 @@
 // (cmd/bitrot-streaming.go:57-59 for writers, :194-196 for readers) — the two passes the
 // reference makes over each shard are one pass over shared-memory tiles here.
 //
-// Work decomposition (all integer/byte work, HBM- and issue-bound; no tensor cores):
-//   CTA      = `eb` erasure blocks, blockDim = 2*(k+r)*eb rounded up to a warp multiple
+// Work decomposition (all integer/byte work, ALU-issue- and HBM-bound; no tensor cores):
+//   CTA      = `eb` erasure blocks (4 in the specialised kernels: one warp per block), blockDim = 2*(k+r)*eb rounded
+//              up to a warp multiple; persistent grid of as many CTAs as fit (7 per SM for RS(12,4))
 //   tile     = 256 bytes of every shard.  Shards start at arbitrary byte offsets of the object
-//              (S = ceil(blockSize/k) is 87382 for RS(12,4)@1MiB) but TMA boxes must start on 16-byte
-//              boundaries, so each row is fetched as its 272-byte 16B-aligned superset ("raw" tile,
-//              cp.async.bulk.tensor with u32 elements; Split's zero padding = TMA out-of-bounds fill)
-//   GF step  = each thread owns an 8-byte column: rows are re-aligned in registers (PRMT with
-//              compile-time selectors when S mod 16 is a template constant), re-stored into the
-//              "aligned" tile for the hash threads, and multiplied -> r outputs -> STS.64 + STG.64
-//   HH step  = two threads per shard stream (64-bit lanes {0,1} / {2,3}); rows of the aligned tile
-//              have a 288-byte pitch so the four streams of a quarter-warp hit disjoint banks.
-//   pipeline = raw tile i+1 is in flight (TMA) while the hash threads chew on aligned tile i; two
-//              CTA barriers per tile, hidden by 6-7 resident CTAs per SM.
+//              (S = ceil(blockSize/k) is 87382 for RS(12,4)@1MiB) but TMA boxes must start on 16-byte boundaries
+//              (tools/tma_probe.cu), so each row is fetched as a 16B-aligned superset ("raw" tile, cp.async.bulk.tensor
+//              with u32 elements: 3-D requests of several rows x eb blocks at a 288-byte pitch for the specialised
+//              encode, one 272-byte 2-D box per row otherwise; Split's zero padding = TMA out-of-bounds fill)
+//   GF step  = each thread owns an 8-byte column: rows are re-aligned in registers (PRMT with compile-time selectors when
+//              S mod 16 is a template constant), re-stored into the "aligned" tile for the hash threads, and multiplied
+//              -> r outputs -> STS.64 + STG.64
+//   HH step  = two threads per shard stream (64-bit lanes {0,1} / {2,3}); rows of the aligned tile have a 288-byte pitch
+//              so the four streams of a quarter-warp hit disjoint banks
+//   pipeline = raw tile i+1 is in flight (TMA) while the hash threads chew on aligned tile i; two CTA barriers per tile
+//   direct   = inputs whose rows are all 16-byte aligned (reconstruct / heal / verify frames, encode with S mod 16 == 0)
+//              skip the raw -> aligned copy: TMA writes the 288-byte-pitch rows the hash threads read, two buffers
+//              alternate, tile i+2 is requested as soon as tile i is consumed
 #pragma once
 #include "ec_device.cuh"
 
