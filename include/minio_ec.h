@@ -136,6 +136,12 @@ int64_t mec_decode_prefer(mec_codec* c, const uint8_t* const* files, const uint8
 /* Erasure.Heal (cmd/erasure-decode.go:317): rebuilds every shard file with out_files[i] != NULL
  * from the readable files (NULL = offline / stale). */
 int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total_length, uint8_t* const* out_files);
+/* Heal of many objects (BASELINE config 4; healObject fan-out of cmd/global-heal.go:152): object o has files[o][0..n),
+ * totals[o], out_files[o][0..n) with mec_heal's meaning.  `pool` holds npool codec handles of the same geometry (each owns
+ * its streams and staging buffers); one host thread per handle pulls objects, so staging, kernels and copy-back of
+ * different objects overlap.  rcs (optional) receives the per-object result; the return value is the first error. */
+int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobjects, const uint8_t* const* const* files,
+                   const int64_t* total_lengths, uint8_t* const* const* out_files, int* rcs);
 
 /* ---- legacy whole-file bitrot (cmd/bitrot-whole.go, BitrotAlgorithm SHA256 / BLAKE2b512 / HighwayHash256) ----
  * Erasure.Encode with wholeBitrotWriters (cmd/bitrot-whole.go:35-45): files[i] receives the raw shard file

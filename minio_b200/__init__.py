@@ -5,7 +5,7 @@ The product is the C-ABI shared library ``libminio_ec.so`` (include/minio_ec.h) 
 There is no CPU implementation here: without the built CUDA library, importing fails loudly.
 """
 from .capi import (BLAKE2B512, HIGHWAYHASH256, HIGHWAYHASH256S, SHA256, Codec, MecError, device_count, lib,
-                   lib_path, selftest)
+                   lib_path, heal_batch, pinned_array, selftest)
 
 __all__ = ["Codec", "MecError", "lib", "lib_path", "device_count", "selftest", "SHA256", "HIGHWAYHASH256",
-           "HIGHWAYHASH256S", "BLAKE2B512"]
+           "HIGHWAYHASH256S", "BLAKE2B512", "heal_batch", "pinned_array"]

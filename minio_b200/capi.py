@@ -60,6 +60,7 @@ def lib():
     L.mec_decode.restype = i64
     L.mec_decode.argtypes = [vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
     L.mec_heal.argtypes = [vp, vp, i64, vp]
+    L.mec_heal_batch.argtypes = [vp, i32, i64, vp, vp, vp, vp]
     L.mec_decode_prefer.restype = i64
     L.mec_decode_prefer.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
     L.mec_shutdown.restype = None
@@ -288,3 +289,36 @@ class Codec:
         if self.m:
             self.rs_encode_shards(shards)
         return shards
+
+
+def pinned_array(nbytes):
+    """uint8 numpy array over page-locked host memory from mec_alloc_pinned (bpool.BytePoolCap's role); never freed by the
+    array — keep it for the life of the process or release it with lib().mec_free_pinned(arr.ctypes.data)."""
+    p = lib().mec_alloc_pinned(max(int(nbytes), 1))
+    if not p:
+        raise MecError(-100, "mec_alloc_pinned")
+    return np.ctypeslib.as_array((C.c_uint8 * int(nbytes)).from_address(p))
+
+
+def heal_batch(pool, objects, outs=None):
+    """mec_heal_batch: `pool` = list of Codec handles of one geometry, `objects` = list of (files, stale, total).
+    Returns the rebuilt shard files per object (None where not stale).  `outs` = preallocated output arrays per object
+    (e.g. pinned_array of bitrot_file_size(total) bytes where stale, None elsewhere); default: fresh pageable arrays."""
+    n = pool[0].n
+    handles = (C.c_void_p * len(pool))(*[c.h for c in pool])
+    keep, fptrs, optrs, outs_all = [], [], [], []
+    for o, (files, stale, total) in enumerate(objects):
+        files = [None if f is None else _u8(f) for f in files]
+        fsz = pool[0].bitrot_file_size(total)
+        obj_outs = outs[o] if outs is not None else [np.zeros(fsz, dtype=np.uint8) if stale[i] else None for i in range(n)]
+        fp, op = _ptrs(files), _ptrs(obj_outs)
+        keep += [files, fp, op]
+        fptrs.append(C.cast(fp, C.c_void_p)); optrs.append(C.cast(op, C.c_void_p)); outs_all.append(obj_outs)
+    nobj = len(objects)
+    fa = (C.c_void_p * nobj)(*fptrs); oa = (C.c_void_p * nobj)(*optrs)
+    totals = (C.c_int64 * nobj)(*[t for _, _, t in objects])
+    rcs = (C.c_int32 * nobj)()
+    rc = lib().mec_heal_batch(handles, len(pool), nobj, fa, totals, oa, rcs)
+    if rc:
+        raise MecError(rc, "mec_heal_batch")
+    return outs_all

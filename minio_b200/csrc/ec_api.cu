@@ -4,10 +4,13 @@
 // H2D -> kernel -> D2H pipeline; *_device entry points run on caller-provided device memory.
 // There is NO CPU fallback anywhere in this file: without a usable GPU every call fails.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <thread>
+#include <vector>
 #include "../../include/minio_ec.h"
 #include "ec_engine.h"
 #include "whole_hash.cuh"
@@ -624,6 +627,36 @@ extern "C" int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total
   std::vector<uint8_t> alive(n), want(n, 0);
   for (int i = 0; i < n; i++) { alive[i] = files[i] != nullptr; want[i] = out_files[i] != nullptr; }
   return reconstruct_range(c, files, g, want.data(), 0, out_files, nullptr, alive.data());
+}
+
+// Batched heal (BASELINE config 4): objects are independent, so a pool of codec handles — each with
+// its own streams and staging buffers — is driven by one host thread per handle; the H2D staging of one object then
+// overlaps the kernel and the D2H of the others (healObject's callers, cmd/global-heal.go:152, do the same with goroutines).
+extern "C" int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobjects, const uint8_t* const* const* files,
+                              const int64_t* totals, uint8_t* const* const* out_files, int* rcs) {
+  if (!pool || npool <= 0 || nobjects < 0 || (nobjects > 0 && (!files || !totals || !out_files))) return MEC_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < npool; i++)
+    if (!pool[i]) return MEC_ERR_INVALID_ARGUMENT;
+  std::atomic<int64_t> next{0};
+  std::atomic<int> first_err{MEC_OK};
+  auto work = [&](int w) {
+    for (;;) {
+      const int64_t o = next.fetch_add(1);
+      if (o >= nobjects) return;
+      const int rc = mec_heal(pool[w], files[o], totals[o], out_files[o]);
+      if (rcs) rcs[o] = rc;
+      if (rc != MEC_OK) {
+        int expected = MEC_OK;
+        first_err.compare_exchange_strong(expected, rc);
+      }
+    }
+  };
+  const int nthreads = static_cast<int>(std::min<int64_t>(npool, nobjects));
+  std::vector<std::thread> th;
+  for (int w = 1; w < nthreads; w++) th.emplace_back(work, w);
+  if (nthreads > 0) work(0);
+  for (auto& t : th) t.join();
+  return first_err.load();
 }
 
 extern "C" int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file_len, int64_t part_len) {

@@ -399,6 +399,32 @@ def test_heal_with_runtime_specialised_kernels(mb, oracle, k, m, stale):
         c.close()
 
 
+def test_heal_batch_over_a_codec_pool(mb, oracle):
+    """mec_heal_batch (BASELINE config 4 shape, scaled down): many objects, different lengths and stale sets, healed through
+    a pool of handles by concurrent host threads; every rebuilt shard file equals the oracle's."""
+    k, m, bs = 16, 4, MiB
+    n = k + m
+    pool = [mb.Codec(k, m, bs) for _ in range(3)]
+    objects, want = [], []
+    for o in range(7):
+        size = [3 * MiB, 5 * MiB + 17, 1, MiB, 2 * MiB + 999999, 777, 4 * MiB][o]
+        data = rand(size, 500 + o)
+        files, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+        stale_set = [(0, 7, 16, 19), (1,), (2, 3), (19,), (0, 1, 2, 3), (5, 17), (4, 8, 12, 16)][o]
+        stale = [i in stale_set for i in range(n)]
+        objects.append(([None if stale[i] else files[i] for i in range(n)], stale, size))
+        want.append((files, stale_set))
+    outs = mb.heal_batch(pool, objects)
+    for (files, stale_set), got in zip(want, outs):
+        for i in range(n):
+            if i in stale_set:
+                assert np.array_equal(got[i], files[i])
+            else:
+                assert got[i] is None
+    for c in pool:
+        c.close()
+
+
 def test_background_specialisation(mb, oracle):
     """Default policy (option jit = -1): the first calls of a new erasure pattern run the generic kernel while NVRTC works on
     a background thread; once the pattern is compiled later calls use the specialised kernel.  Same bytes either way."""

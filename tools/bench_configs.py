@@ -191,9 +191,56 @@ def sha256_sweep(k, m, sizes, total_bytes):
         del src, par, dig
 
 
+def heal_batch_case(nobj=32, obj_mib=64, pools=(1, 2, 3, 4), pinned=True):
+    """BASELINE config 4 through the HOST boundary (per-GPU slice, scaled to nobj objects): mec_heal_batch over a pool of
+    codec handles — frames come from (pinned or pageable) host memory, healed shard files go back to it."""
+    import time
+    k, m, bs = 16, 4, 1 << 20
+    n = k + m
+    stale_set = (0, 7, 16, 19)
+    size = obj_mib << 20
+    enc = mb.Codec(k, m, bs)
+    rng = np.random.default_rng(4)
+    objects, ref = [], []
+    for o in range(nobj):
+        data = rng.integers(0, 256, size, dtype=np.uint8)
+        files = enc.encode(data)
+        stale = [i in stale_set for i in range(n)]
+        if pinned:
+            src = []
+            for i in range(n):
+                if stale[i]:
+                    src.append(None)
+                else:
+                    a = mb.pinned_array(files[i].size); a[:] = files[i]; src.append(a)
+        else:
+            src = [None if stale[i] else files[i] for i in range(n)]
+        objects.append((src, stale, size))
+        ref.append(files)
+    fsz = enc.bitrot_file_size(size)
+    enc.close()
+    outs_pre = [[mb.pinned_array(fsz) if i in stale_set else None for i in range(n)] for _ in range(nobj)] if pinned else None
+    for npool in pools:
+        pool = [mb.Codec(k, m, bs) for _ in range(npool)]
+        mb.heal_batch(pool, objects[:max(2, npool)], None if outs_pre is None else outs_pre[:max(2, npool)])  # warm: buffers, specialised kernel
+        time.sleep(1.0)
+        t0 = time.perf_counter()
+        outs = mb.heal_batch(pool, objects, outs_pre)
+        dt = time.perf_counter() - t0
+        ok = all(np.array_equal(outs[o][i], ref[o][i]) for o in range(nobj) for i in stale_set)
+        print(json.dumps({"config": "4-host: RS(16,4) heal batch through mec_heal_batch, %d objects x %d MiB, stale %s" % (nobj, obj_mib, list(stale_set)),
+                          "pool": npool, "host_memory": "pinned" if pinned else "pageable", "seconds": dt, "GiB_per_s_object": nobj * size / GiB / dt, "bit_exact_vs_encode": bool(ok)}), flush=True)
+        for c in pool:
+            c.close()
+
+
 if __name__ == "__main__":
     MiB = 1 << 20
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "healbatch":
+        heal_batch_case(pinned=True)
+        heal_batch_case(pools=(2,), pinned=False)
+        sys.exit(0)
     if only == "gen":   # generic (runtime-matrix) kernel numbers only
         reconstruct_case("gen r=4", 12, 4, MiB, 3552, {0, 1, 2, 3}, 3, 0)
         reconstruct_case("gen r=2", 12, 4, MiB, 3552, {0, 1}, 3, 0)
