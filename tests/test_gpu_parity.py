@@ -399,6 +399,24 @@ def test_heal_with_runtime_specialised_kernels(mb, oracle, k, m, stale):
         c.close()
 
 
+@pytest.mark.parametrize("k,m", [(12, 4), (8, 8)])
+def test_warp_autonomous_variant(mb, oracle, k, m):
+    """Option use_auto = 1 (k + m == 16: one warp per erasure block, no CTA barriers in the steady state; measured slower,
+    off by default) must still produce the reference bytes — for the misaligned (12,4) and the 16-byte aligned (8,8) shards."""
+    bs, size = MiB, 3 * MiB + 123
+    data = rand(size, 31 + k)
+    want, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    c = mb.Codec(k, m, bs)
+    c.set_option("use_auto", 1)
+    c.set_option("no_rows3d", 1)
+    files = c.encode(data)
+    for i in range(k + m):
+        assert np.array_equal(files[i], want[i]), i
+    out, _ = c.decode([None, None] + files[2:], 0, size, size)
+    assert np.array_equal(out, data)
+    c.close()
+
+
 def test_heal_batch_over_a_codec_pool(mb, oracle):
     """mec_heal_batch (BASELINE config 4 shape, scaled down): many objects, different lengths and stale sets, healed through
     a pool of handles by concurrent host threads; every rebuilt shard file equals the oracle's."""
