@@ -222,9 +222,11 @@ def main():
                    "note": "NCCL scatter from rank 0, timed apart from the encode kernel"}
         del recv
 
-    # ---- spot verification against the oracle (outside the timed region)
+    # ---- cpu_baseline leg, part 1 (N = 1 only, like the timing of the oracle further down): the oracle as CHECKER of
+    # three blocks of the device-resident output and one block of the end-to-end output, outside every timed region
     verified = None
-    if rank == 0:
+    oracle_leg = rank == 0 and world == 1 and not args.no_cpu
+    if oracle_leg:
         import oracle_lib as o
         o.build()
         verified = True
@@ -264,7 +266,7 @@ def main():
             dt = float(t.item())
         e2e = {"value": world * eb * BS * args.steps / GiB / dt, "unit": "GiB/s", "h2d_bytes_per_step": eb * BS,
                "d2h_bytes_per_step": eb * (M * S + (K + M) * 32), "sample": f"{eb} blocks per step per GPU, pinned host buffers"}
-        if rank == 0 and verified:
+        if oracle_leg and verified:
             b = eb - 1
             sh = o.encode_data(K, M, h_src[b * BS:(b + 1) * BS].numpy(), fast=True)
             verified &= bool(np.array_equal(h_par.numpy()[(b * M) * S:(b * M + 1) * S], sh[K]))
