@@ -192,6 +192,10 @@ int64_t mec_get_stat(const mec_codec* c, const char* name);
  * during an NVRTC compile lets libnvrtc's exit handlers run under the compiling thread); later calls of the library
  * keep working with the kernels already in the cache.  Also registered with atexit() after the first background compile. */
 void mec_shutdown(void);
+/* Build check of the run-time specialisation (no device needed): NVRTC-compiles the fused kernel for the r x k matrix `coef`
+ * (align = S mod 16 of the inputs, eb = erasure blocks per CTA or 0, rows3d / hash_outputs as the engine would pass them)
+ * without loading it.  Returns the cubin size, 0 when the compile fails (log in mec_last_error), -1 without libnvrtc. */
+int64_t mec_jit_compile_check(int k, int r, const uint8_t* coef, int align, int eb, int rows3d, int hash_outputs);
 /* number of kernels launched by this codec so far (bench.py's gpu_launches) */
 int64_t mec_launch_count(const mec_codec* c);
 

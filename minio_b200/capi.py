@@ -63,6 +63,8 @@ def lib():
     L.mec_heal_batch.argtypes = [vp, i32, i64, vp, vp, vp, vp]
     L.mec_decode_prefer.restype = i64
     L.mec_decode_prefer.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
+    L.mec_jit_compile_check.restype = i64
+    L.mec_jit_compile_check.argtypes = [i32, i32, vp, i32, i32, i32, i32]
     L.mec_shutdown.restype = None
     L.mec_shutdown.argtypes = []
     import atexit

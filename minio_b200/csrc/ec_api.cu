@@ -175,6 +175,11 @@ extern "C" int64_t mec_get_stat(const mec_codec* c, const char* name) {
 }
 extern "C" void mec_shutdown(void) { mec::jit_shutdown(); }
 
+extern "C" int64_t mec_jit_compile_check(int k, int r, const uint8_t* coef, int align, int eb, int rows3d, int hash_outputs) {
+  if (k < 1 || k > kMaxK || r < 1 || r > kMaxR || !coef || align < 0 || align > 15 || eb < 0) return MEC_ERR_INVALID_ARGUMENT;
+  return mec::jit_compile_check(k, r, coef, align, eb, rows3d != 0, hash_outputs != 0);
+}
+
 extern "C" int64_t mec_launch_count(const mec_codec* c) { return (c && c->eng) ? c->eng->launches() : 0; }
 
 static int require_streaming(mec_codec* c) {

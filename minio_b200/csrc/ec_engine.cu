@@ -168,10 +168,11 @@ void jit_quiesce() {
 }
 
 // NVRTC-instantiate the kernel template for one concrete matrix; returns a cudaKernel_t or nullptr
-void* compile_specialised(const JitSpec& sp) {
+// load == false stops after NVRTC (no device needed): the CPU-side check that the embedded headers still specialise
+void* compile_specialised(const JitSpec& sp, bool load = true) {
   NvrtcApi& api = nvrtc_api();
   if (!api.ok) return nullptr;
-  if (cudaSetDevice(sp.device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (load && cudaSetDevice(sp.device) != cudaSuccess) { cudaGetLastError(); return nullptr; }
   const int k = sp.k, r = sp.r;
   void* result = nullptr;
   std::string src = "#include \"ec_kernel.cuh\"\nnamespace mec {\nstruct JitMat { static constexpr int K = " + std::to_string(k) +
@@ -203,6 +204,10 @@ void* compile_specialised(const JitSpec& sp) {
     if (api.cubin_size(prog, &sz) == NVRTC_SUCCESS && sz > 0 && api.lowered(prog, expr, &lname) == NVRTC_SUCCESS) {
       std::vector<char> cubin(sz);
       api.cubin(prog, cubin.data());
+      if (!load) {
+        api.destroy(&prog);
+        return reinterpret_cast<void*>(static_cast<uintptr_t>(sz));  // compiled: cubin size as a non-null token
+      }
       cudaLibrary_t lib = nullptr;
       cudaKernel_t kern = nullptr;
       if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
@@ -264,6 +269,12 @@ void jit_worker_main() {
 }  // namespace
 
 void jit_shutdown() { jit_quiesce(); }
+
+int64_t jit_compile_check(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out) {
+  if (!nvrtc_api().ok) return -1;
+  JitSpec sp{0, k, r, align, eb_t, rows3d, hash_out, std::vector<uint8_t>(coef, coef + static_cast<size_t>(k) * r)};
+  return static_cast<int64_t>(reinterpret_cast<uintptr_t>(compile_specialised(sp, false)));
+}
 
 int64_t Engine::jit_compiles() const {
   JitGlobals& g = jit_globals();

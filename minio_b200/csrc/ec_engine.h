@@ -85,6 +85,8 @@ class Engine {
 
 // stop background specialisation and wait for a compile in flight (mec_shutdown)
 void jit_shutdown();
+// NVRTC-compile (not load) the kernel specialised for `coef`; cubin bytes, 0 on a compile error, -1 without libnvrtc
+int64_t jit_compile_check(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out);
 
 // grow-only device / pinned buffers
 struct DevBuf {

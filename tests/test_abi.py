@@ -104,3 +104,24 @@ def test_shutdown_is_callable_without_a_device():
         pytest.skip("would switch background specialisation off for the GPU tests that share this process")
     L.mec_shutdown()
     L.mec_shutdown()
+
+
+@pytest.mark.parametrize("case", ["decode-hashed", "decode-get", "encode-10-4"])
+def test_nvrtc_specialisation_compiles_without_a_device(case, oracle):
+    """The kernel headers embedded in the library must still instantiate under NVRTC for a concrete matrix: decode rows of
+    RS(12,4) with four data shards lost (aligned frames, 4 blocks per CTA; with and without digests of the rebuilt shards)
+    and the parity rows of a geometry that has no compiled kernel.  Compile only — loading needs a GPU."""
+    import minio_b200.capi as capi
+    L = capi.lib()
+    if case.startswith("decode"):
+        present = [0] * 4 + [1] * 12
+        rows, _ = oracle.decode_rows(12, 4, present, [0, 1, 2, 3])
+        k, r, align, hash_out = 12, 4, 0, 1 if case == "decode-hashed" else 0
+    else:
+        k, r, align, hash_out = 10, 4, (-(-(1 << 20) // 10)) % 16, 1
+        rows = np.array(oracle.rs_matrix(10, 4), dtype=np.uint8).reshape(14, 10)[10:]
+    rows = np.ascontiguousarray(rows, dtype=np.uint8)
+    n = L.mec_jit_compile_check(k, r, rows.ctypes.data, align, 4, 0, hash_out)
+    if n == -1:
+        pytest.skip("libnvrtc not available")
+    assert n > 0, L.mec_last_error().decode()
