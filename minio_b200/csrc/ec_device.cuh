@@ -13,161 +13,238 @@
 
 namespace mec {
 
-#ifndef MEC_XTIME
-#define MEC_XTIME 0
-#endif
 #ifndef MEC_HH_VARIANT
 #define MEC_HH_VARIANT 0
 #endif
 
 // ---------------------------------------------------------------- small helpers
 template <class F, int... I>
-__device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
+__host__ __device__ __forceinline__ void static_for_impl(F&& f, std::integer_sequence<int, I...>) {
   (f(std::integral_constant<int, I>{}), ...);
 }
 template <int N, class F>
-__device__ __forceinline__ void static_for(F&& f) {
+__host__ __device__ __forceinline__ void static_for(F&& f) {
   static_for_impl(static_cast<F&&>(f), std::make_integer_sequence<int, N>{});
 }
 
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+__host__ __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+#ifdef __CUDA_ARCH__
   uint32_t d;
   asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
   return d;
+#else  // host restatement (tests/cpp/test_gfplan.cu runs the compile-time GF plans on the CPU)
+  const uint64_t pool = (static_cast<uint64_t>(b) << 32) | a;
+  uint32_t d = 0;
+  for (int i = 0; i < 4; i++) {
+    const uint32_t s4 = (sel >> (4 * i)) & 0xfu;
+    uint32_t byte = static_cast<uint32_t>(pool >> (8 * (s4 & 7u))) & 0xffu;
+    if (s4 & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;
+    d |= byte << (8 * i);
+  }
+  return d;
+#endif
 }
 
 // ---------------------------------------------------------------- packed GF(2^8)
-// multiply each of the 4 packed field elements by x (i.e. by 2) modulo x^8+x^4+x^3+x^2+1.
-// Three instruction mixes with different ALU-pipe / FMA-pipe weight (measured in tools/ubench2.cu):
-//   V=0  PRMT sign-replicate + 2 AND (+ shift)      : 3 ALU ops, FMA pipe almost idle
-//   V=1  AND + integer SUB + ADD + high-half multiply: 1 ALU op, ~8 FMA-pipe cycles
-//   V=2  AND + XOR + shift + high-half multiply      : 2 ALU ops, ~6 FMA-pipe cycles
-template <int V>
-__device__ __forceinline__ uint32_t gf_xtime4_v(uint32_t a) {
-  if constexpr (V == 0) {
-    const uint32_t m = prmt(a, 0u, 0xba98u);  // 0xff per byte whose msb is set
-    return ((a & 0x7f7f7f7fu) << 1) ^ (m & 0x1d1d1d1du);
-  } else if constexpr (V == 1) {
-    const uint32_t t = a & 0x7f7f7f7fu;
-    uint32_t h;
-    asm("sub.u32 %0, %1, %2;" : "=r"(h) : "r"(a), "r"(t));  // == a & 0x80808080, kept as an integer op on purpose
-    return (t + t) ^ __umulhi(h, 0x1du << 25);
-  } else {
-    const uint32_t h = a & 0x80808080u;
-    return ((a ^ h) << 1) ^ __umulhi(h, 0x1du << 25);
-  }
+// multiply each of the 4 packed field elements by x (i.e. by 2) modulo x^8+x^4+x^3+x^2+1: PRMT sign-replicate gives
+// 0xff per byte whose msb is set, two ANDs and a shift finish it — 3 ALU-pipe ops, FMA pipe almost idle.  (Variants that
+// move work to the FMA pipe through IMAD.HI were measured in round 1 and lose: profiles/r1_pipe_microbench.md.)
+__host__ __device__ __forceinline__ uint32_t gf_xtime4(uint32_t a) {
+  const uint32_t m = prmt(a, 0u, 0xba98u);
+  return ((a & 0x7f7f7f7fu) << 1) ^ (m & 0x1d1d1d1du);
 }
-// Division by x: a * x^-1 = (a >> 1) ^ (lsb ? 0x8e : 0), x^-1 = x^7+x^3+x^2+x.  The low bits are peeled off with one
-// AND, removed with an integer subtract and turned into the reduction term with a plain 32-bit multiply (both cheap
-// FMA-pipe ops; 0/1 bytes times 0x8e cannot carry), so a Horner step in x^-1 costs 2 ALU-pipe ops where the
-// doubling above costs 3.  Used with the coefficient decomposition c = sum_b c'_b x^-b (see GfStaticApply).
-__device__ __forceinline__ uint32_t gf_xdiv4(uint32_t a) {
-  const uint32_t l = a & 0x01010101u;
-  uint32_t e;
-  asm("sub.u32 %0, %1, %2;" : "=r"(e) : "r"(a), "r"(l));  // clears the low bit of every byte (kept as an integer op)
-  return (e >> 1) ^ (l * 0x8eu);
-}
-#ifndef MEC_GF_DIV
-#define MEC_GF_DIV 0   // 1: Horner in x^-1 (gf_xdiv4), 0: Horner in x (gf_xtime4).  Measured: the x^-1 form saves an ALU op per step but c*x^7 is denser than the (sparse) RS coefficients, so it loses overall.
-#endif
 
 // One Horner step  acc*x ^ x_terms  in 3 ALU-pipe ops + 1 FMA-pipe op: the byte-msb mask comes from PRMT, the
 // doubling is a plain 32-bit add whose cross-byte carry-in bit is masked INSIDE the final LOP3
 // ((a+a) & 0xfefefefe == (a & 0x7f7f7f7f) << 1), and the reduction mask is folded into the LOP3 that adds the terms.
-__device__ __forceinline__ uint32_t gf_xtime_add4(uint32_t a, uint32_t x_terms) {
+__host__ __device__ __forceinline__ uint32_t gf_xtime_add4(uint32_t a, uint32_t x_terms) {
   const uint32_t m = prmt(a, 0u, 0xba98u);  // 0xff per byte whose msb is set
   const uint32_t a2 = a + a;
   const uint32_t y = (m & 0x1d1d1d1du) ^ x_terms;
   return (a2 & 0xfefefefeu) ^ y;
 }
-#ifndef MEC_FUSED_STEP
-#define MEC_FUSED_STEP 1   // 1: gf_xtime_add4 (shipped), 0: separate doubling + XOR accumulation
-#endif
-
-#ifndef MEC_XMIX_NUM
-#define MEC_XMIX_NUM 0   // of every MEC_XMIX_DEN Horner steps, this many use the FMA-heavy variant 1
-#endif
-#ifndef MEC_XMIX_DEN
-#define MEC_XMIX_DEN 4
-#endif
-__device__ __forceinline__ uint32_t gf_xtime4(uint32_t a) { return gf_xtime4_v<MEC_XTIME>(a); }
 
 // Compile-time specialised  out[j] = XOR_t  coef(j,t) (x) in[t]   on packed words.
-// Horner over the bit planes of the coefficients: 7 doublings per OUTPUT word (not per input), and
-// the plane sums are assembled from "four Russians" combinations of input triples, so a
-// (12 -> 4) product costs ~210 integer ops per 4-byte column instead of 48 table multiplies.
-// bit of coefficient c that multiplies Horner plane `plane`: in the x^-1 scheme plane b carries x^-b and
-// c = sum_b c'_b x^-b with c'_b = bit (7-b) of c*x^7; in the x scheme it is simply bit `plane` of c.
-__host__ __device__ constexpr int plane_bit(uint8_t c, int plane) {
-#if MEC_GF_DIV
-  return (gf_mul(c, 0x80) >> (7 - plane)) & 1;
-#else
-  return (c >> plane) & 1;
-#endif
-}
+//
+// (1) Horner over the bit planes of the coefficients: out_j = sum_b x^b P_jb with P_jb the XOR of the inputs whose
+//     coefficient has bit b set — doublings are paid per OUTPUT word (at most 7), never per input, and a chain starts at
+//     the highest plane that has a term at all.
+// (2) Plane sums are assembled from "four Russians" XOR combinations of small input groups.
+// (3) Subset-sum change of basis.  The systematic Vandermonde matrix of reedsolomon.New is a Lagrange interpolation at
+//     the points 0..k+m-1, and addition in GF(2^8) is XOR, so M[r ^ t][c ^ t] = M[r][c] whenever the data columns and
+//     the parity rows are both closed under ^t: every aligned 2^L x 2^L block is an XOR-circulant.  With
+//     Z = [[1,0],[1,1]]^(x)L (y_i = XOR of x_j over the bit-subsets j of i; Z is its own inverse over GF(2)),
+//     Z * circulant * Z is "subset-triangular": only 3^L of its 4^L entries survive and the sums of circulant entries
+//     that appear off the full-degree corner have low degree.  RS(12,4): of the 48 eight-bit coefficients 27 remain,
+//     three of them eight-bit — 16 doublings instead of 28 and a third of the XOR terms, ~80 ALU ops per 12-word column
+//     instead of ~134.  The inputs are transformed with L*2^(L-1) XORs per block, the outputs likewise afterwards.
+//     Decode matrices of erasure patterns that are unions of aligned blocks (e.g. shards {0,1,2,3}) keep the structure.
+//     The level L (0 = plain) and the group size of (2) are chosen per matrix by a compile-time op count.
+__host__ __device__ constexpr bool bit_subset(int j, int i) { return (j & ~i) == 0; }
 
-#ifndef MEC_GF_GROUP
-#define MEC_GF_GROUP 4   // inputs per "four Russians" group (3 or 4); 4 needs ~13 % fewer XORs for RS(12,4)
-#endif
+template <class MAT, int L>
+struct GfXform {
+  static constexpr int K = MAT::K, R = MAT::R, B = 1 << L, KB = K / B * B, RB = R / B * B;
+  struct Tab {
+    uint8_t c[R > 0 ? R : 1][K > 0 ? K : 1];  // transformed matrix, natural (block-major) input order
+    uint8_t ord[K > 0 ? K : 1];               // inputs in type-major order (same subset index of every block adjacent)
+    signed char top[R > 0 ? R : 1];              // highest plane with a term, -1 = row is zero
+  };
+  __host__ __device__ static constexpr Tab build() {
+    Tab t{};
+    for (int r = 0; r < R; r++)
+      for (int c = 0; c < K; c++) {
+        uint8_t v = 0;
+        // C' = Z C Z:  C'[r][c] = XOR over rows i subset-of r and columns j superset-of c (inside their blocks)
+        for (int i = (r < RB ? r / B * B : r); i <= r; i++) {
+          if (r < RB ? !bit_subset(i % B, r % B) : i != r) continue;
+          for (int j = c; j < (c < KB ? c / B * B + B : c + 1); j++) {
+            if (c < KB ? !bit_subset(c % B, j % B) : j != c) continue;
+            v ^= MAT::coef(i, j);
+          }
+        }
+        t.c[r][c] = v;
+      }
+    int n = 0;
+    for (int pc = L; pc >= 0; pc--)  // subset indices with many bits first: the "block sums" carry the high-degree coefficients
+      for (int typ = B - 1; typ >= 0; typ--) {
+        int bits = 0;
+        for (int q = 0; q < L; q++) bits += (typ >> q) & 1;
+        if (bits != pc) continue;
+        for (int blk = 0; blk < K / B; blk++) t.ord[n++] = static_cast<uint8_t>(blk * B + typ);
+      }
+    for (int c = KB; c < K; c++) t.ord[n++] = static_cast<uint8_t>(c);
+    for (int r = 0; r < R; r++) {
+      int top = -1;
+      for (int c = 0; c < K; c++)
+        for (int b = 0; b < 8; b++)
+          if ((t.c[r][c] >> b) & 1) top = b > top ? b : top;
+      t.top[r] = static_cast<signed char>(top);
+    }
+    return t;
+  }
+  static constexpr Tab tab = build();
 
-template <class MAT>  // MAT::K, MAT::R, static constexpr uint8_t MAT::coef(j, t)
-struct GfStaticApply {
-  static constexpr int K = MAT::K, R = MAT::R, GS = MEC_GF_GROUP, G = (K + GS - 1) / GS, NC = 1 << GS;
-  // index of the XOR combination of group g that feeds output j at Horner plane `plane`
+  // index of the XOR combination of group g (inputs ord[GS*g ...]) that feeds row j at Horner plane `plane`
+  template <int GS>
   __host__ __device__ static constexpr int combo_index(int j, int g, int plane) {
     int idx = 0;
     for (int q = 0; q < GS; q++)
-      if (GS * g + q < K && plane_bit(MAT::coef(j, GS * g + q), plane)) idx |= 1 << q;
+      if (GS * g + q < K && ((tab.c[j][tab.ord[GS * g + q]] >> plane) & 1)) idx |= 1 << q;
     return idx;
   }
-  __device__ __forceinline__ static void run(const uint32_t (&in)[K], uint32_t (&out)[R]) {
+  // ALU-op estimate of run<GS>(): butterflies + distinct multi-input combinations + Horner steps
+  template <int GS>
+  __host__ __device__ static constexpr int cost() {
+    constexpr int G = (K + GS - 1) / GS;
+    int ops = (K / B + R / B) * (L * B / 2);
+    bool used[G > 0 ? G : 1][1 << GS] = {};
+    for (int j = 0; j < R; j++)
+      for (int plane = tab.top[j]; plane >= 0; plane--) {
+        int n = 0;
+        for (int g = 0; g < G; g++) {
+          const int idx = combo_index<GS>(j, g, plane);
+          if (idx) { n++; used[g][idx] = true; }
+        }
+        if (plane == tab.top[j]) ops += n > 1 ? n / 2 : 0;
+        else ops += 3 + n / 2;  // PRMT + 2 LOP3 absorb one term, every further LOP3 two more
+      }
+    for (int g = 0; g < G; g++)
+      for (int idx = 1; idx < (1 << GS); idx++)
+        if (used[g][idx] && (idx & (idx - 1))) ops += (idx == (1 << GS) - 1 && GS == 4) ? 2 : 1;
+    return ops;
+  }
+
+  template <int GS>
+  __host__ __device__ __forceinline__ static void run(const uint32_t (&in)[K], uint32_t (&out)[R]) {
+    constexpr int G = (K + GS - 1) / GS, NC = 1 << GS;
+    uint32_t y[K];
+#pragma unroll
+    for (int t = 0; t < K; t++) y[t] = in[t];
+    static_for<L>([&](auto l_) {  // subset sums inside every block of B inputs
+      constexpr int bit = 1 << decltype(l_)::value;
+      static_for<KB>([&](auto t_) {
+        constexpr int t = decltype(t_)::value;
+        if constexpr ((t % B) & bit) y[t] ^= y[t ^ bit];
+      });
+    });
     uint32_t cmb[G][NC];
     static_for<G>([&](auto g_) {
       constexpr int g = decltype(g_)::value;
       cmb[g][0] = 0u;
       static_for<NC - 1>([&](auto i_) {
         constexpr int idx = decltype(i_)::value + 1;
-        constexpr int low = idx & -idx;              // lowest set bit
+        constexpr int low = idx & -idx;  // lowest set bit
         constexpr int q = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : 3;
-        constexpr int t = GS * g + q;
-        const uint32_t v = (t < K) ? in[t < K ? t : 0] : 0u;
-        cmb[g][idx] = cmb[g][idx & (idx - 1)] ^ v;   // unused combinations are dead code
+        constexpr int pos = GS * g + q;
+        if constexpr (pos < K) {
+          constexpr int src = tab.ord[pos];
+          cmb[g][idx] = cmb[g][idx & (idx - 1)] ^ y[src];  // unused combinations are dead code
+        } else {
+          cmb[g][idx] = cmb[g][idx & (idx - 1)];
+        }
       });
     });
     static_for<R>([&](auto j_) {
       constexpr int j = decltype(j_)::value;
+      constexpr int top = tab.top[j];
       uint32_t acc = 0u;
-      static_for<8>([&](auto bb_) {
-        constexpr int step = decltype(bb_)::value;  // 0 = innermost plane of the Horner scheme
-        constexpr int plane = 7 - step;
-#if MEC_FUSED_STEP && !MEC_GF_DIV
+      static_for<(top >= 0 ? top + 1 : 0)>([&](auto s_) {
+        constexpr int plane = top - decltype(s_)::value;
         uint32_t terms = 0u;
         static_for<G>([&](auto g_) {
           constexpr int g = decltype(g_)::value;
-          constexpr int idx = combo_index(j, g, plane);
+          constexpr int idx = combo_index<GS>(j, g, plane);
           if constexpr (idx != 0) terms ^= cmb[g][idx];
         });
-        if constexpr (step != 0) acc = gf_xtime_add4(acc, terms);
+        if constexpr (plane != top) acc = gf_xtime_add4(acc, terms);
         else acc = terms;
-#else
-#if MEC_GF_DIV
-        if constexpr (step != 0) acc = gf_xdiv4(acc);
-#else
-        if constexpr (step != 0) {
-          constexpr bool fma_heavy = ((plane * R + j) % MEC_XMIX_DEN) < MEC_XMIX_NUM;
-          acc = fma_heavy ? gf_xtime4_v<1>(acc) : gf_xtime4_v<MEC_XTIME>(acc);
-        }
-#endif
-        static_for<G>([&](auto g_) {
-          constexpr int g = decltype(g_)::value;
-          constexpr int idx = combo_index(j, g, plane);
-          if constexpr (idx != 0) acc ^= cmb[g][idx];
-        });
-#endif
       });
       out[j] = acc;
     });
+    static_for<L>([&](auto l_) {  // back from subset sums to the outputs themselves (Z is an involution)
+      constexpr int bit = 1 << decltype(l_)::value;
+      static_for<RB>([&](auto j_) {
+        constexpr int j = decltype(j_)::value;
+        if constexpr ((j % B) & bit) out[j] ^= out[j ^ bit];
+      });
+    });
   }
+};
+
+#ifndef MEC_GF_LEVEL
+#define MEC_GF_LEVEL -1   // -1: choose the transform level per matrix by op count; 0..3: force it (A/B measurements)
+#endif
+#ifndef MEC_GF_GROUP
+#define MEC_GF_GROUP 0    // 0: choose 3 or 4 inputs per "four Russians" group by op count; 3 / 4: force it
+#endif
+
+template <class MAT>  // MAT::K, MAT::R, static constexpr uint8_t MAT::coef(j, t)
+struct GfStaticApply {
+  static constexpr int K = MAT::K, R = MAT::R;
+  template <int L>
+  __host__ __device__ static constexpr int level_cost() {
+    if constexpr ((1 << L) > K || (1 << L) > R) return 1 << 30;
+    else {
+      const int c3 = GfXform<MAT, L>::template cost<3>(), c4 = GfXform<MAT, L>::template cost<4>();
+      return MEC_GF_GROUP == 3 ? c3 : (MEC_GF_GROUP == 4 ? c4 : (c3 < c4 ? c3 : c4));
+    }
+  }
+  __host__ __device__ static constexpr int choose_level() {
+    constexpr int forced = MEC_GF_LEVEL < 0 ? 0 : MEC_GF_LEVEL;
+    if (MEC_GF_LEVEL >= 0) return ((1 << forced) > K || (1 << forced) > R) ? 0 : forced;
+    int best = 0, bc = level_cost<0>();
+    if (level_cost<1>() < bc) { best = 1; bc = level_cost<1>(); }
+    if (level_cost<2>() < bc) { best = 2; bc = level_cost<2>(); }
+    if (level_cost<3>() < bc) { best = 3; bc = level_cost<3>(); }
+    return best;
+  }
+  static constexpr int kLevel = choose_level();
+  using X = GfXform<MAT, kLevel>;
+  static constexpr int kGroup = MEC_GF_GROUP == 3 || MEC_GF_GROUP == 4 ? MEC_GF_GROUP
+                                                                        : (X::template cost<3>() < X::template cost<4>() ? 3 : 4);
+  static constexpr int kOps = kGroup == 3 ? X::template cost<3>() : X::template cost<4>();
+  __host__ __device__ __forceinline__ static void run(const uint32_t (&in)[K], uint32_t (&out)[R]) { X::template run<kGroup>(in, out); }
 };
 
 // parity rows of reedsolomon.New(K, M): coef(j, t) = M[K + j][t]

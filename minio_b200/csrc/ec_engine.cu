@@ -192,12 +192,11 @@ void* compile_specialised(const JitSpec& sp, bool load = true) {
   const char* expr = expr_s.c_str();
   if (api.create(&prog, src.c_str(), "mec_jit.cu", 4, bodies, names) != NVRTC_SUCCESS) return nullptr;
   api.add_name(prog, expr);
-  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device", "-DMEC_XTIME=" MEC_STR(MEC_XTIME),
+  const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-default-device",
                         "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
                         "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS),
-                        "-DMEC_GF_DIV=" MEC_STR(MEC_GF_DIV), "-DMEC_GF_GROUP=" MEC_STR(MEC_GF_GROUP),
-                        "-DMEC_FUSED_STEP=" MEC_STR(MEC_FUSED_STEP)};
-  nvrtcResult rc = api.compile(prog, 10, opts);
+                        "-DMEC_GF_LEVEL=" MEC_STR(MEC_GF_LEVEL), "-DMEC_GF_GROUP=" MEC_STR(MEC_GF_GROUP)};
+  nvrtcResult rc = api.compile(prog, 8, opts);
   if (rc == NVRTC_SUCCESS) {
     size_t sz = 0;
     const char* lname = nullptr;
@@ -432,7 +431,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     for (int j = 0; j < d.r; j++)
       for (int t = 0; t < d.k; t++) {
         const uint8_t c = d.coef[static_cast<size_t>(j) * d.k + t];
-        p.coef[j][t] = MEC_GF_DIV ? gf_mul(c, 0x80) : c;  // x^-1 Horner: planes are the bits of c*x^7
+        p.coef[j][t] = c;
       }
   }
 

@@ -234,12 +234,8 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
     // expand coefficient bytes into AND-masks: s_masks[(t*rpad + j)*8 + bit]
     for (int i = tid; i < k * rpad * 8; i += nthr) {
       const int bit = i & 7, j = (i >> 3) % rpad, t = (i >> 3) / rpad;
-      const uint32_t c = j < r ? p.coef[j][t] : 0u;  // MEC_GF_DIV: the host passes c*x^7, plane b is bit 7-b
-#if MEC_GF_DIV
-      s_masks[i] = 0u - ((c >> (7 - bit)) & 1u);
-#else
+      const uint32_t c = j < r ? p.coef[j][t] : 0u;
       s_masks[i] = 0u - ((c >> bit) & 1u);
-#endif
     }
   }
   __syncthreads();
@@ -467,16 +463,8 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
               uint32_t al = pl[j][7], ah = ph[j][7];
 #pragma unroll
               for (int b = 6; b >= 0; b--) {
-#if MEC_GF_DIV
-                al = gf_xdiv4(al) ^ pl[j][b];
-                ah = gf_xdiv4(ah) ^ ph[j][b];
-#elif MEC_FUSED_STEP
                 al = gf_xtime_add4(al, pl[j][b]);
                 ah = gf_xtime_add4(ah, ph[j][b]);
-#else
-                al = gf_xtime4(al) ^ pl[j][b];
-                ah = gf_xtime4(ah) ^ ph[j][b];
-#endif
               }
               store_out(j0 + j, make_uint2(al, ah));
             }
