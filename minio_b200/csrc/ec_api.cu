@@ -126,7 +126,13 @@ static int ensure_engine(mec_codec* c) {
   std::unique_ptr<Engine> e(new Engine(c->device));
   int rc = e->init();
   if (rc) return rc;
-  for (auto& s : c->slots) MEC_CUDA_OK(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+  for (auto& s : c->slots)
+    if (cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking) != cudaSuccess) {
+      set_last_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(cudaGetLastError()));
+      for (auto& q : c->slots)
+        if (q.st) { cudaStreamDestroy(q.st); q.st = nullptr; }
+      return MEC_ERR_CUDA;
+    }
   c->eng = std::move(e);
   return MEC_OK;
 }
@@ -216,7 +222,7 @@ static int encode_device_locked(mec_codec* c, const uint8_t* d_src, int64_t len,
     d.nblocks = 1; d.S = static_cast<int32_t>(St);
     d.in_base = d_src + nfull * bs; d.in_block_stride = round_up(tail, 16); d.in_block_len = tail;
     d.out = d_parity + nfull * c->m * pitch;
-    d.digests = d_digests + nfull * c->n * 32;
+    d.digests = d_digests ? d_digests + nfull * c->n * 32 : nullptr;  // NULL = parity only, for the tail block too
     int rc = c->eng->launch_fused(d, c->opt, st);
     if (rc) return rc;
   }
@@ -505,6 +511,7 @@ extern "C" int mec_reconstruct_device(mec_codec* c, const uint8_t* const* d_fram
   if (n > kMaxShards || k > kMaxK) return MEC_ERR_UNSUPPORTED;
   const int64_t S = c->S();
   if ((frame_pitch & 15) || frame_pitch < 32 + S) return MEC_ERR_INVALID_ARGUMENT;
+  if (d_corrupt && !d_digests) return MEC_ERR_INVALID_ARGUMENT;  // the digest check runs in the hash threads: no digests, no bitrot verdict
   int chosen[kMaxShards], nch = 0;
   std::vector<uint8_t> present(n, 0);
   for (int i = 0; i < n && nch < k; i++)

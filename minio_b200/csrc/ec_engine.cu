@@ -48,6 +48,7 @@ constexpr int kStaticEb = 4;  // erasure blocks per CTA of the compile-time spec
 struct StaticEntry {
   int k, m, sm16;
   KernelFn fast3d;    // TMA, S mod 16 == sm16, eb == kStaticEb, one 3-D request per tile
+  KernelFn fast3d_auto;  // same, warp-autonomous pipeline (k + m == 16 and misaligned rows only), else nullptr
   KernelFn fast_auto, aligned_auto;  // warp-autonomous pipeline (k + m == 16 only), else nullptr
   KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb
   KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb
@@ -57,6 +58,7 @@ struct StaticEntry {
 static const StaticEntry kStaticTable[] = {
 #define X(K, M, A)                                                                                      \
   {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, false, true>,                          \
+   (K + M == 16 && A != 0) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16 && A != 0), true> : nullptr, \
    (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16)> : nullptr, \
    (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16)> : nullptr,          \
    fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, false>,                                        \
@@ -96,11 +98,8 @@ struct NvrtcApi {
   decltype(&nvrtcGetProgramLog) log = nullptr;
   bool ok = false;
 };
-static NvrtcApi& nvrtc_api() {
-  static NvrtcApi api;
-  static bool tried = false;
-  if (tried) return api;
-  tried = true;
+static NvrtcApi load_nvrtc() {
+  NvrtcApi api;
   for (const char* name : {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"}) {
     api.h = dlopen(name, RTLD_NOW | RTLD_LOCAL);
     if (api.h) break;
@@ -112,6 +111,12 @@ static NvrtcApi& nvrtc_api() {
   MEC_SYM(lowered, nvrtcGetLoweredName); MEC_SYM(log_size, nvrtcGetProgramLogSize); MEC_SYM(log, nvrtcGetProgramLog);
 #undef MEC_SYM
   api.ok = api.create && api.destroy && api.add_name && api.compile && api.cubin_size && api.cubin && api.lowered && api.log_size && api.log;
+  return api;
+}
+// reached from the background compiler, from synchronous jit = 1 callers and from mec_jit_compile_check: the function-local
+// static is initialised exactly once (thread-safe since C++11), so no caller can see a half-filled table
+static NvrtcApi& nvrtc_api() {
+  static NvrtcApi api = load_nvrtc();
   return api;
 }
 
@@ -525,7 +530,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   if (se) {
     const int sm16 = static_cast<int>(d.S & 15);
     if (!use_tma) fn = se->bytewise;
-    else if (rows3d) fn = se->fast3d;
+    else if (rows3d) fn = (opt.use_auto && se->fast3d_auto && !direct) ? se->fast3d_auto : se->fast3d;
     else if (eb == kStaticEb && sm16 == se->sm16) fn = (opt.use_auto && se->fast_auto) ? se->fast_auto : se->fast;
     else if (eb == kStaticEb && sm16 == 0) fn = (opt.use_auto && se->aligned_auto) ? se->aligned_auto : se->aligned;
     else fn = se->runtime;

@@ -134,6 +134,9 @@ static_assert(rows_per_request_3d(8, 0, 4) == 8 && raw_row_3d(8, 0, 4) == kTile,
 #ifndef MEC_MIN_BLOCKS
 #define MEC_MIN_BLOCKS 3
 #endif
+#ifndef MEC_L2_PREFETCH
+#define MEC_L2_PREFETCH 1   // tiles of L2 prefetch distance ahead of the TMA load (3-D fetch path); 0 = off
+#endif
 
 // one 8-byte column of raw row `row` whose logical byte 0 sits `A` bytes into the row
 template <int A>
@@ -162,8 +165,9 @@ __device__ __forceinline__ uint2 load_col_rt(const uint8_t* row, uint32_t a) {
 // (0 = every row 16B-aligned), kAlignRuntime = per-row table in the params.  EB_T: erasure blocks
 // per CTA when fixed at compile time (0 = runtime).  AUTO: k + r == 16, i.e. one warp owns exactly
 // one erasure block (32 columns, 16 streams x 2 hash threads): the GF -> HH hand-off is then
-// warp-local (__syncwarp) and the only CTA-wide event is "raw tile consumed", tracked by an arrival
-// counter whose last arriver issues the next TMA batch — no __syncthreads in the steady state.
+// warp-local (__syncwarp) and the only CTA-wide event is "raw tile consumed": every warp arrives on a
+// plain mbarrier as soon as its lanes hold their columns in registers, and the TMA-issuing lane of warp 0
+// waits for that phase before it requests the next tile — no __syncthreads in the steady state.
 // ROWS3D: all k rows x eb blocks of a tile arrive with ONE 3-D TMA request (x, block, row) instead of k requests;
 // only the last tiles of a shard, whose box would cross the row stride, fall back to per-row requests (which also
 // provide Split's zero padding through out-of-bounds fill).  Needs a compile-time ALIGN and EB_T.
@@ -215,7 +219,6 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   // bytes [256, 288) of an aligned / output row are bank-skew padding nobody reads or writes: the mbarriers sit in row 0's
   // (DIRECT input rows are written by TMA over their full pitch, so there it is the first output row, or 128 spare bytes)
   uint64_t* bars = reinterpret_cast<uint64_t*>(DIRECT ? (r > 0 ? s_par + kTile : s_par) : s_clean + kTile);
-  uint32_t* s_arrive = reinterpret_cast<uint32_t*>(bars + 2);
   const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
 
   const int32_t S = p.S;
@@ -226,8 +229,8 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
     if (tid == 0) {
       mbar_init(smem_u32(&bars[0]), 1);
       if constexpr (DIRECT) mbar_init(smem_u32(&bars[1]), 1);
+      if constexpr (AUTO) mbar_init(smem_u32(&bars[2]), static_cast<uint32_t>(nthr >> 5));  // "raw tile consumed": one arrival per warp
       fence_barrier_init();
-      *s_arrive = 0;
     }
   }
   if constexpr (!GF::kIsStatic) {
@@ -287,6 +290,14 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
               for (int gq = 0; gq < kGroups; gq++)
                 tma_load_3d(dst0 + static_cast<uint32_t>(gq * kRG) * group_bytes, &maps.m[1],
                             i * (kTile / 4) + group_shift_3d(gq, kSm3, kRG) / 4, static_cast<int32_t>(b0), gq * kRG, bar);
+#if MEC_L2_PREFETCH
+              // the tile after this one goes to L2 now: its load, one tile period from here, then costs an L2 hit, not a DRAM trip
+              if (i + MEC_L2_PREFETCH < p.tiles_3d) {
+#pragma unroll
+                for (int gq = 0; gq < kGroups; gq++)
+                  tma_prefetch_3d(&maps.m[1], (i + MEC_L2_PREFETCH) * (kTile / 4) + group_shift_3d(gq, kSm3, kRG) / 4, static_cast<int32_t>(b0), gq * kRG);
+              }
+#endif
             }
           } else {               // last tiles of the shard: per-row boxes, zero padding via out-of-bounds fill
             if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * kRaw3);
@@ -321,9 +332,11 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
     auto issue_tile = [&](int i) { issue_tile_at(i, b0, nb, 0, 1); };
 
     if constexpr (USE_TMA) {
-      // AUTO: later groups are pre-issued by the last arriver of the previous group's final tile
-      if (warp0 && (!AUTO || g == static_cast<int64_t>(blockIdx.x))) {
+      if (warp0) {
         if (elect_one() && ntiles > 0) {
+          if constexpr (AUTO) {  // the previous group's last raw tile must have been read by every warp
+            if (g != static_cast<int64_t>(blockIdx.x)) mbar_wait(smem_u32(&bars[2]), (it - 1u) & 1u);
+          }
           issue_tile(0);
           if constexpr (DIRECT) {
             if (ntiles > 1) issue_tile(1);
@@ -337,12 +350,14 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
     }
 
     // ---- HH step: packets [8j, 8j+8) of every stream, from the aligned + output tiles
-    auto hh_step = [&](int j) {
-      if (hh_live) {
+    // FAST: a full tile of a full group — all eight packets present, no remainder, every hash thread live
+    auto hh_step = [&](int j, auto fast_) {
+      constexpr bool FAST = decltype(fast_)::value;
+      if (FAST ? hh_thread : hh_live) {
         const uint32_t flip = (DIRECT && ((it + static_cast<uint32_t>(j)) & 1u)) ? hh_flip : 0u;
         const uint32_t addr = hh_addr + flip;
         const int q0 = 8 * j;
-        if (q0 + 8 <= npk) {
+        if (FAST || q0 + 8 <= npk) {
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const uint4 v = lds128(addr + 32 * q);
@@ -355,36 +370,23 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
             hh_update(hs, pack64(v.x, v.y), pack64(v.z, v.w));
           }
         }
-        if (j == ntiles - 1 && rem) {
+        if (!FAST && j == ntiles - 1 && rem) {
           const uint8_t* tail = hh_row + flip + ((npk * 32) & (kTile - 1));
           hh_remainder(hs, h, rem, [&](int idx) -> uint32_t { return tail[idx]; });
         }
       }
     };
 
-    // ---------------- main tile loop (general form)
-    for (int i = 0; i < ntiles; i++) {
+    // ---------------- one tile.  The steady state (FAST: every byte of the tile inside the shard, every block of the group
+    // present) carries no bounds predicates and no partial stores; only the last tile of a shard and the last, partial
+    // group of a launch take the general form.
+    auto tile_body = [&](int i, auto fast_) {
+      constexpr bool FAST = decltype(fast_)::value;
       const uint32_t sel = DIRECT ? ((it + static_cast<uint32_t>(i)) & 1u) : 0u;
       if constexpr (DIRECT) mbar_wait(smem_u32(&bars[sel]), ((it + static_cast<uint32_t>(i)) >> 1) & 1u);
       else if constexpr (USE_TMA) mbar_wait(smem_u32(&bars[0]), (it + i) & 1u);
 
       // ---- GF step on tile i: re-align, re-store, multiply, store
-      auto raw_consumed = [&]() {  // AUTO: count this warp's arrival; the last arriver refills the raw tile
-        uint32_t last = 0;
-        if ((tid & 31) == 0) last = (atomicAdd(s_arrive, 1u) % static_cast<uint32_t>(nthr >> 5)) == static_cast<uint32_t>((nthr >> 5) - 1);
-        last = __shfl_sync(0xffffffffu, last, 0);
-        if (last) {
-          if (i + 1 < ntiles) {
-            if (elect_one()) issue_tile(i + 1);
-          } else if (g + gridDim.x < ngroups) {
-            if (elect_one()) {  // first tile of this CTA's next group
-              const int64_t b0n = (g + gridDim.x) * eb;
-              issue_tile_at(0, b0n, (p.nblocks - b0n) < eb ? static_cast<int>(p.nblocks - b0n) : eb, 0, 1);
-            }
-          }
-          __syncwarp();
-        }
-      };
       for (int c = tid; c < ncol; c += nthr) {
         const int e = c >> 5, x8 = c & 31;
         const uint8_t* rcol = s_raw + sel * buf_bytes + e * rawp + x8 * 8;
@@ -392,12 +394,12 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
         uint8_t* prow = s_par + static_cast<uint32_t>(e) * par_blk + x8 * 8;
         const int64_t xg = static_cast<int64_t>(i) * kTile + x8 * 8;
         uint8_t* gout = p.out + (b0 + e) * r * p.out_pitch + xg;
-        const bool full = e < nb && xg + 8 <= S;
-        const bool part = e < nb && xg < S && !full;
+        const bool full = FAST || (e < nb && xg + 8 <= S);
+        const bool part = !FAST && e < nb && xg < S && !full;
         auto store_out = [&](int j, uint2 o) {
           *reinterpret_cast<uint2*>(prow + static_cast<uint32_t>(j) * par_row) = o;
           uint8_t* gp = gout + j * p.out_pitch;
-          if (full) {
+          if (FAST || full) {
             *reinterpret_cast<uint2*>(gp) = o;
           } else if (part) {
             const uint64_t w = pack64(o.x, o.y);
@@ -416,10 +418,10 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
             if constexpr (!DIRECT) *reinterpret_cast<uint2*>(crow + t * kRowPitch) = v;
           });
           if constexpr (AUTO && USE_TMA) {
-            // the raw tile is dead as soon as every lane holds its column in registers: signal it
-            // now so the next TMA batch overlaps the GF arithmetic as well as the hashing
+            // the raw tile is dead as soon as every lane holds its column in registers: release it now (one arrival per
+            // warp on the "consumed" mbarrier), the issuing lane of warp 0 collects the arrivals before the next TMA batch
             __syncwarp();
-            raw_consumed();
+            if (elect_one()) mbar_arrive(smem_u32(&bars[2]));
           }
           if constexpr (R > 0) {
             uint32_t olo[R], ohi[R];
@@ -473,7 +475,7 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
       }
       if constexpr (DIRECT) {
         if (r > 0) __syncthreads();  // (A) output rows complete
-        hh_step(i);
+        hh_step(i, fast_);
         __syncthreads();             // (B) everyone is done with this buffer (and the output rows): refill it two tiles ahead
         if (i + 2 < ntiles) {
           if constexpr (ROWS3D) {
@@ -486,11 +488,18 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
             __syncwarp();
           }
         }
-        continue;
+        return;
       }
       if constexpr (AUTO && USE_TMA) {
+        static_assert(!AUTO || GF::kIsStatic, "the warp-autonomous pipeline is instantiated for compile-time matrices only");
         __syncwarp();  // (A) this warp's aligned + output rows are complete
-        if constexpr (!GF::kIsStatic) raw_consumed();
+        if (warp0 && i + 1 < ntiles) {
+          if (elect_one()) {
+            mbar_wait(smem_u32(&bars[2]), (it + static_cast<uint32_t>(i)) & 1u);  // every warp holds its columns of tile i
+            issue_tile_at(i + 1, b0, nb, 0, 1);
+          }
+          __syncwarp();
+        }
       } else {
         __syncthreads();  // (A) aligned + output tiles complete; raw tile fully consumed
         if (i + 1 < ntiles) {  // refill the raw tile while the hash threads work on the aligned one
@@ -508,10 +517,16 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
         }
       }
 
-      hh_step(i);
+      hh_step(i, fast_);
       if constexpr (AUTO && USE_TMA) __syncwarp();  // (B) this warp's rows may be overwritten
       else __syncthreads();                          // (B) aligned + output tiles may be overwritten
-    }
+    };
+    static_assert(kTile == 256, "tile shift");
+    const int nfast = (nb == eb) ? (S >> 8) : 0;
+#pragma unroll 1
+    for (int i = 0; i < nfast; i++) tile_body(i, std::integral_constant<bool, true>{});
+#pragma unroll 1
+    for (int i = nfast; i < ntiles; i++) tile_body(i, std::integral_constant<bool, false>{});
 
     // ---------------- finalisation
     {
