@@ -59,9 +59,19 @@ int64_t mec_shard_file_offset(const mec_codec* c, int64_t start_offset, int64_t 
 int64_t mec_bitrot_shard_file_size(int64_t size, int64_t shard_size, int algo); /* bitrotShardFileSize cmd/bitrot.go:156 */
 int64_t mec_ceil_frac(int64_t numerator, int64_t denominator);               /* ceilFrac cmd/utils.go:689 */
 
-/* ---- pinned host memory for the byte pool (internal/bpool/bpool.go:52,68 AllocAligned) ------ */
+/* ---- pinned host memory for the byte pool (internal/bpool/bpool.go:25-93; AllocAligned :52,68) ------
+ * mec_alloc_pinned: page-locked memory, wherever the calling thread runs.  mec_alloc_pinned_on: page-locked memory on the
+ * NUMA node of CUDA device `device` (/sys/bus/pci/devices/<bdf>/numa_node; mbind + first touch + cudaHostRegister) — on a
+ * multi-socket box every GPU should stream from the memory behind its own root port.  Both are released with
+ * mec_free_pinned.  mec_device_numa_node returns that node (-1 unknown); mec_bind_thread_to_device restricts the calling
+ * thread to the CPUs of that node (never beyond its current affinity mask) and returns the node, or -1 when it could not.
+ * mec_is_pinned: 1 when `p` is page-locked memory known to CUDA (the host-buffer entry points DMA straight from / into it). */
 void* mec_alloc_pinned(size_t bytes);
+void* mec_alloc_pinned_on(int device, size_t bytes);
 void mec_free_pinned(void* p);
+int mec_device_numa_node(int device);
+int mec_bind_thread_to_device(int device);
+int mec_is_pinned(const void* p);
 
 /* ---- fused block encode: the body of Erasure.EncodeData (cmd/erasure-coding.go:77-91) plus
  * the HighwayHash256 of every shard that streamingBitrotWriter.Write computes
@@ -105,6 +115,8 @@ int mec_reconstruct_frames(mec_codec* c, const uint8_t* const* frames, int64_t n
  * `flags`: MEC_RECONSTRUCT_DATA_ONLY = ReconstructData semantics (parity never rebuilt);
  * MEC_RECONSTRUCT_NO_OUTPUT_DIGESTS = the rebuilt shards are not hashed (GetObject consumes their bytes only,
  * cmd/erasure-decode.go:283-289; the k shards read are still hashed and checked), their digest slots stay untouched.
+ * d_corrupt != NULL requires d_digests != NULL (the digest check runs in the hash threads; MEC_ERR_INVALID_ARGUMENT otherwise);
+ * with d_digests == NULL nothing is hashed or verified.
  * Asynchronous on `cuda_stream`; the fail-over policy stays with the caller (see mec_reconstruct_frames). */
 #define MEC_RECONSTRUCT_DATA_ONLY 1
 #define MEC_RECONSTRUCT_NO_OUTPUT_DIGESTS 2
@@ -119,6 +131,16 @@ int mec_reconstruct_device(mec_codec* c, const uint8_t* const* d_frames, int64_t
  * mec_bitrot_shard_file_size(mec_shard_file_size(len)) bytes.  Fails with MEC_ERR_WRITE_QUORUM
  * when fewer than `write_quorum` writers are online.  Returns bytes consumed. */
 int64_t mec_encode(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, int write_quorum);
+/* The same call in the shape streamingBitrotWriter.Write actually has (cmd/bitrot-streaming.go:57-69: w.Write(hash), then
+ * w.Write(p) — the shard bytes are never copied next to their digest): the k data shards stay inside `src`, where Split
+ * aliased them (cmd/erasure-coding.go:81), and only what the GPU produced comes back —
+ *   files[k..n)   : complete part.N images of the parity drives (NULL = offline), written by DMA straight from device memory
+ *   data_digests  : digest of data shard i of block b at data_digests + (b*k + i)*32; writer i emits, per block,
+ *                   {data_digests[b][i], src + b*block_size + i*S_b (zero padded to S_b)}  (writev / the cgo writeHashed stub)
+ *   files[0..k)   : only tested for NULL (offline writers count against write_quorum)
+ * No assembly copy exists anywhere on this path.  Returns bytes consumed. */
+int64_t mec_encode_sg(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* data_digests,
+                      int write_quorum);
 
 /* Erasure.Decode (cmd/erasure-decode.go:239) over streaming bitrot readers: writes object bytes
  * [offset, offset+length) of a part of `total_length` bytes to dst.  files[i] NULL = offline.
@@ -136,10 +158,17 @@ int64_t mec_decode_prefer(mec_codec* c, const uint8_t* const* files, const uint8
 /* Erasure.Heal (cmd/erasure-decode.go:317): rebuilds every shard file with out_files[i] != NULL
  * from the readable files (NULL = offline / stale). */
 int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total_length, uint8_t* const* out_files);
+/* Heal with its `prefer` argument and the bitrot side-band.  Returns MEC_OK, or MEC_ERR_FILE_CORRUPT when the stale shards
+ * WERE rebuilt and written but a source reader failed its digest on the way — Heal's derr (cmd/erasure-decode.go:338-341,366;
+ * healObject aborts the part on it, cmd/erasure-healing.go:603-608); corrupt[i] (optional, n bytes) names those readers.
+ * mec_heal is this call with prefer = NULL, corrupt = NULL and returns the same codes. */
+int mec_heal_prefer(mec_codec* c, const uint8_t* const* files, const uint8_t* prefer, int64_t total_length,
+                    uint8_t* const* out_files, uint8_t* corrupt);
 /* Heal of many objects (BASELINE config 4; healObject fan-out of cmd/global-heal.go:152): object o has files[o][0..n),
  * totals[o], out_files[o][0..n) with mec_heal's meaning.  `pool` holds npool codec handles of the same geometry (each owns
  * its streams and staging buffers); one host thread per handle pulls objects, so staging, kernels and copy-back of
- * different objects overlap.  rcs (optional) receives the per-object result; the return value is the first error. */
+ * different objects overlap.  rcs (optional) receives the per-object result (MEC_ERR_FILE_CORRUPT = healed, a source reader
+ * failed its digest); the return value is the first result that is neither MEC_OK nor MEC_ERR_FILE_CORRUPT. */
 int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobjects, const uint8_t* const* const* files,
                    const int64_t* total_lengths, uint8_t* const* const* out_files, int* rcs);
 

@@ -51,6 +51,14 @@ def lib():
     L.mec_alloc_pinned.argtypes = [C.c_size_t]
     L.mec_free_pinned.argtypes = [vp]
     L.mec_free_pinned.restype = None
+    L.mec_alloc_pinned_on.restype = vp
+    L.mec_alloc_pinned_on.argtypes = [i32, C.c_size_t]
+    L.mec_device_numa_node.argtypes = [i32]
+    L.mec_bind_thread_to_device.argtypes = [i32]
+    L.mec_is_pinned.argtypes = [vp]
+    L.mec_encode_sg.restype = i64
+    L.mec_encode_sg.argtypes = [vp, vp, i64, vp, vp, i32]
+    L.mec_heal_prefer.argtypes = [vp, vp, vp, i64, vp, vp]
     L.mec_encode_blocks.argtypes = [vp, vp, i64, vp, vp]
     L.mec_encode_blocks_device.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     L.mec_reconstruct_frames.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp]
@@ -186,6 +194,21 @@ class Codec:
             raise MecError(rc, "mec_encode")
         return files
 
+    def encode_sg(self, src, online=None, write_quorum=0):
+        """mec_encode_sg: -> (files, data_digests).  files[i] is None for data drives (their frames are the caller's own
+        source slices behind data_digests[b, i]) and the complete part.N image for online parity drives."""
+        src = _u8(src)
+        fsz = self.bitrot_file_size(src.size)
+        nb = -(-src.size // self.block_size)
+        online = [True] * self.n if online is None else online
+        marker = np.zeros(1, dtype=np.uint8)  # data drives: only NULL / non-NULL is looked at
+        files = [(np.zeros(fsz, dtype=np.uint8) if i >= self.k else marker) if online[i] else None for i in range(self.n)]
+        dd = np.zeros((max(nb, 1), self.k, 32), dtype=np.uint8)
+        rc = lib().mec_encode_sg(self.h, src.ctypes.data if src.size else None, src.size, _ptrs(files), dd.ctypes.data, write_quorum)
+        if rc < 0:
+            raise MecError(rc, "mec_encode_sg")
+        return [f if i >= self.k else None for i, f in enumerate(files)], dd[:nb]
+
     def stat(self, name):
         return lib().mec_get_stat(self.h, name.encode())
 
@@ -200,11 +223,20 @@ class Codec:
             raise MecError(rc, "mec_decode")
         return dst[:length], hint.value
 
-    def heal(self, files, stale, total):
+    def heal(self, files, stale, total, prefer=None, report=False):
+        """Erasure.Heal.  Like the reference, bitrot met in a source reader does not stop the rebuild but is reported:
+        report=False raises MecError(errFileCorrupt) after the healed files were produced (Heal's derr); report=True
+        returns (outs, rc, corrupt[n])."""
         files = [None if f is None else _u8(f) for f in files]
         fsz = self.bitrot_file_size(total)
         outs = [np.zeros(fsz, dtype=np.uint8) if stale[i] else None for i in range(self.n)]
-        rc = lib().mec_heal(self.h, _ptrs(files), total, _ptrs(outs))
+        corrupt = np.zeros(self.n, dtype=np.uint8)
+        pf = None if prefer is None else np.asarray(prefer, dtype=np.uint8)
+        rc = lib().mec_heal_prefer(self.h, _ptrs(files), None if pf is None else pf.ctypes.data, total, _ptrs(outs), corrupt.ctypes.data)
+        if report:
+            if rc and rc != -7:
+                raise MecError(rc, "mec_heal")
+            return outs, rc, corrupt
         if rc:
             raise MecError(rc, "mec_heal")
         return outs
@@ -293,10 +325,11 @@ class Codec:
         return shards
 
 
-def pinned_array(nbytes):
-    """uint8 numpy array over page-locked host memory from mec_alloc_pinned (bpool.BytePoolCap's role); never freed by the
-    array — keep it for the life of the process or release it with lib().mec_free_pinned(arr.ctypes.data)."""
-    p = lib().mec_alloc_pinned(max(int(nbytes), 1))
+def pinned_array(nbytes, device=None):
+    """uint8 numpy array over page-locked host memory from mec_alloc_pinned (bpool.BytePoolCap's role) — with `device`, on the
+    NUMA node of that GPU (mec_alloc_pinned_on); never freed by the array — keep it for the life of the process or release
+    it with lib().mec_free_pinned(arr.ctypes.data)."""
+    p = lib().mec_alloc_pinned(max(int(nbytes), 1)) if device is None else lib().mec_alloc_pinned_on(int(device), max(int(nbytes), 1))
     if not p:
         raise MecError(-100, "mec_alloc_pinned")
     return np.ctypeslib.as_array((C.c_uint8 * int(nbytes)).from_address(p))

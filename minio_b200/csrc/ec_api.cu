@@ -38,8 +38,28 @@ static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * 
 
 constexpr int kSlots = 3;
 
+// grow-only page-locked host staging (digests and digest verdicts: small, read by the host right after a stream drains)
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return MEC_OK;
+    release();
+    const size_t want = n + (n >> 2) + 4096;
+    MEC_CUDA_OK(cudaHostAlloc(&p, want, cudaHostAllocPortable));
+    cap = want;
+    return MEC_OK;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
 struct Slot {
-  DevBuf src, out, dig, aux;
+  DevBuf src, out, dig, aux, flags;  // aux: survivor arena of a reconstruct chunk / shard files of the whole-file path
+  PinBuf hdig, hflags;
   cudaStream_t st = nullptr;
 };
 
@@ -52,7 +72,6 @@ struct mec_codec {
   EngineOptions opt;
   std::mutex mu;
   Slot slots[kSlots];
-  DevBuf in_files[kMaxShards];  // reconstruct: staged survivor frames, indexed by shard number
   DevBuf flags;
   // boundary counters (mec_get_stat)
   int64_t st_blocks_encoded = 0, st_blocks_read = 0, st_shards_rebuilt = 0, st_corrupt = 0, st_h2d = 0, st_d2h = 0;
@@ -86,15 +105,6 @@ extern "C" int64_t mec_bitrot_shard_file_size(int64_t size, int64_t shard_size, 
   return ceil_frac(size, shard_size) * 32 + size;
 }
 
-extern "C" void* mec_alloc_pinned(size_t bytes) {
-  void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
-  return p;
-}
-extern "C" void mec_free_pinned(void* p) {
-  if (p) cudaFreeHost(p);
-}
-
 extern "C" int mec_codec_new(int k, int m, int64_t block_size, int algo, int device, mec_codec** out) {
   if (!out) return MEC_ERR_INVALID_ARGUMENT;
   *out = nullptr;
@@ -115,6 +125,7 @@ extern "C" int mec_codec_new(int k, int m, int64_t block_size, int algo, int dev
   if (const char* e = getenv("MEC_USE_AUTO")) c->opt.use_auto = atoi(e);
   if (const char* e = getenv("MEC_JIT")) c->opt.jit = atoi(e);
   if (const char* e = getenv("MEC_NO_ROWS3D")) c->opt.no_rows3d = atoi(e);
+  if (const char* e = getenv("MEC_STATIC_GROUPS")) c->opt.static_groups = atoi(e);
   *out = c.release();
   return MEC_OK;
 }
@@ -143,9 +154,9 @@ extern "C" void mec_codec_free(mec_codec* c) {
   cudaSetDevice(c->device);
   for (auto& s : c->slots) {
     if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
-    s.src.release(); s.out.release(); s.dig.release(); s.aux.release();
+    s.src.release(); s.out.release(); s.dig.release(); s.aux.release(); s.flags.release();
+    s.hdig.release(); s.hflags.release();
   }
-  for (auto& b : c->in_files) b.release();
   c->flags.release();
   delete c;
 }
@@ -162,6 +173,7 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else if (!strcmp(name, "jit")) c->opt.jit = static_cast<int>(v);
   else if (!strcmp(name, "no_rows3d")) c->opt.no_rows3d = static_cast<int>(v);
   else if (!strcmp(name, "chunk_blocks")) c->opt.chunk_blocks = v;
+  else if (!strcmp(name, "static_groups")) c->opt.static_groups = static_cast<int>(v);
   else return MEC_ERR_INVALID_ARGUMENT;
   return MEC_OK;
 }
@@ -252,6 +264,58 @@ static int64_t pick_chunk_blocks(const mec_codec* c) {
   return cb < 1 ? 1 : cb;
 }
 
+// One chunk of the host-buffer encode pipeline, as the sinks below see it.
+struct EncChunk {
+  int64_t b0, nb;      // erasure blocks [b0, b0 + nb) of the call
+  int64_t nfull;       // of which full (block_size) blocks; the call's short tail block, if in this chunk, follows them
+  int64_t tail;        // bytes of that tail block (0 = none)
+  Slot* s;             // device buffers of this chunk: src (object bytes), out (parity at `pitch`), dig ([nb][n][32])
+  int64_t pitch;
+};
+
+// The 3-slot H2D -> fused kernel -> D2H pipeline behind every host-buffer encode entry point.  `enqueue(ch)` adds the
+// chunk's device->host copies to ch.s->st right behind the kernel; `retire(ch)` runs on the host once that stream has
+// drained (digest scatter into frames).  On any error every slot stream is drained before returning, so no copy is
+// still writing into caller memory (or reading freed staging) when the caller sees the error code.
+template <class Enqueue, class Retire>
+static int encode_pipeline(mec_codec* c, const uint8_t* src, int64_t len, Enqueue&& enqueue, Retire&& retire) {
+  const int64_t bs = c->block_size, S = c->S(), pitch = round_up(S, 16);
+  const int64_t nall = ceil_frac(len, bs), chunk = pick_chunk_blocks(c);
+  struct Drain {
+    mec_codec* c;
+    ~Drain() { for (auto& s : c->slots) if (s.st) cudaStreamSynchronize(s.st); }
+  } drain{c};
+  EncChunk inflight[kSlots];
+  bool busy[kSlots] = {};
+  int si = 0, rc;
+  for (int64_t b0 = 0; b0 < nall; b0 += chunk, si = (si + 1) % kSlots) {
+    Slot& s = c->slots[si];
+    MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+    if (busy[si]) { retire(inflight[si]); busy[si] = false; }
+    EncChunk ch;
+    ch.b0 = b0; ch.nb = std::min(chunk, nall - b0); ch.s = &s; ch.pitch = pitch;
+    const int64_t off = b0 * bs, bytes = std::min(len - off, ch.nb * bs);
+    ch.nfull = bytes / bs; ch.tail = bytes % bs;
+    if ((rc = s.src.ensure(static_cast<size_t>(round_up(bytes, 16) + 256)))) return rc;
+    if ((rc = s.out.ensure(static_cast<size_t>(ch.nb * std::max(c->m, 1) * pitch)))) return rc;
+    if ((rc = s.dig.ensure(static_cast<size_t>(ch.nb * c->n * 32)))) return rc;
+    MEC_CUDA_OK(cudaMemcpyAsync(s.src.p, src + off, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, s.st));
+    if ((rc = encode_device_locked(c, static_cast<const uint8_t*>(s.src.p), bytes, static_cast<uint8_t*>(s.out.p), pitch,
+                                   static_cast<uint8_t*>(s.dig.p), s.st)))
+      return rc;
+    if ((rc = enqueue(ch))) return rc;
+    inflight[si] = ch;
+    busy[si] = true;
+  }
+  for (int q = 0; q < kSlots; q++, si = (si + 1) % kSlots) {  // oldest first
+    MEC_CUDA_OK(cudaStreamSynchronize(c->slots[si].st));
+    if (busy[si]) { retire(inflight[si]); busy[si] = false; }
+  }
+  c->st_blocks_encoded += nall;
+  c->st_h2d += len;
+  return MEC_OK;
+}
+
 extern "C" int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* parity, uint8_t* digests) {
   NvtxRange nvtx("mec_encode_blocks");
   if (!c || len < 0) return MEC_ERR_INVALID_ARGUMENT;
@@ -261,44 +325,107 @@ extern "C" int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, 
   if (c->S() >= (1ll << 31)) return MEC_ERR_UNSUPPORTED;
   std::lock_guard<std::mutex> lk(c->mu);
   MEC_CUDA_OK(cudaSetDevice(c->device));
-  const int64_t bs = c->block_size, S = c->S(), pitch = round_up(S, 16);
-  const int64_t nall = ceil_frac(len, bs), chunk = pick_chunk_blocks(c);
-  int si = 0;
-  for (int64_t b0 = 0; b0 < nall; b0 += chunk, si = (si + 1) % kSlots) {
-    Slot& s = c->slots[si];
-    const int64_t nb = std::min(chunk, nall - b0);
-    const int64_t off = b0 * bs, bytes = std::min(len - off, nb * bs);
-    MEC_CUDA_OK(cudaStreamSynchronize(s.st));
-    if ((rc = s.src.ensure(static_cast<size_t>(round_up(bytes, 16) + 256)))) return rc;
-    if ((rc = s.out.ensure(static_cast<size_t>(nb * std::max(c->m, 1) * pitch)))) return rc;
-    if ((rc = s.dig.ensure(static_cast<size_t>(nb * c->n * 32)))) return rc;
-    MEC_CUDA_OK(cudaMemcpyAsync(s.src.p, src + off, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, s.st));
-    rc = encode_device_locked(c, static_cast<const uint8_t*>(s.src.p), bytes, static_cast<uint8_t*>(s.out.p), pitch,
-                              static_cast<uint8_t*>(s.dig.p), s.st);
-    if (rc) return rc;
-    const int64_t nfull = bytes / bs, tail = bytes % bs;
-    if (c->m > 0 && nfull > 0)
-      MEC_CUDA_OK(cudaMemcpy2DAsync(parity + b0 * c->m * S, static_cast<size_t>(S), s.out.p, static_cast<size_t>(pitch),
-                                    static_cast<size_t>(S), static_cast<size_t>(nfull * c->m), cudaMemcpyDeviceToHost, s.st));
-    if (c->m > 0 && tail > 0) {
-      const int64_t St = ceil_frac(tail, c->k);
-      MEC_CUDA_OK(cudaMemcpy2DAsync(parity + (b0 + nfull) * c->m * S, static_cast<size_t>(S),
-                                    static_cast<uint8_t*>(s.out.p) + nfull * c->m * pitch, static_cast<size_t>(pitch),
-                                    static_cast<size_t>(St), static_cast<size_t>(c->m), cudaMemcpyDeviceToHost, s.st));
-    }
-    MEC_CUDA_OK(cudaMemcpyAsync(digests + b0 * c->n * 32, s.dig.p, static_cast<size_t>(nb * c->n * 32),
-                                cudaMemcpyDeviceToHost, s.st));
-  }
-  for (auto& s : c->slots) MEC_CUDA_OK(cudaStreamSynchronize(s.st));
-  c->st_blocks_encoded += nall;
-  c->st_h2d += len;
-  c->st_d2h += nall * (c->m * S + c->n * 32);
+  const int64_t S = c->S();
+  rc = encode_pipeline(
+      c, src, len,
+      [&](const EncChunk& ch) -> int {
+        Slot& s = *ch.s;
+        if (c->m > 0 && ch.nfull > 0)
+          MEC_CUDA_OK(cudaMemcpy2DAsync(parity + ch.b0 * c->m * S, static_cast<size_t>(S), s.out.p, static_cast<size_t>(ch.pitch),
+                                        static_cast<size_t>(S), static_cast<size_t>(ch.nfull * c->m), cudaMemcpyDeviceToHost, s.st));
+        if (c->m > 0 && ch.tail > 0) {
+          const int64_t St = ceil_frac(ch.tail, c->k);
+          MEC_CUDA_OK(cudaMemcpy2DAsync(parity + (ch.b0 + ch.nfull) * c->m * S, static_cast<size_t>(S),
+                                        static_cast<uint8_t*>(s.out.p) + ch.nfull * c->m * ch.pitch, static_cast<size_t>(ch.pitch),
+                                        static_cast<size_t>(St), static_cast<size_t>(c->m), cudaMemcpyDeviceToHost, s.st));
+        }
+        MEC_CUDA_OK(cudaMemcpyAsync(digests + ch.b0 * c->n * 32, s.dig.p, static_cast<size_t>(ch.nb * c->n * 32),
+                                    cudaMemcpyDeviceToHost, s.st));
+        return MEC_OK;
+      },
+      [](const EncChunk&) {});
+  if (rc) return rc;
+  c->st_d2h += ceil_frac(len, c->block_size) * (c->m * S + c->n * 32);
   return MEC_OK;
 }
 
-// Erasure.Encode + streaming bitrot writers: frames assembled on the host from the caller's own
-// data bytes (Split aliasing) and the GPU's parity + digests.
-extern "C" int64_t mec_encode(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, int write_quorum) {
+// Frame sinks of Erasure.Encode.  files[i] is the part.N image of drive i: ([32 B digest][shard bytes])* with full frames
+// of 32 + S bytes and one short last frame.  Everything that is bulk moves by DMA straight from device memory into the
+// caller's frames (2-D copies: one row per erasure block); only the 32-byte digests go through a pinned staging buffer and
+// are scattered by the host while the next chunks are in flight.  No pageable temporaries, no assembly memcpy of shard bytes.
+//   parity drives:  frames of drive k+j come from the kernel's parity rows
+//   data drives:    with_data = true copies the data shards back from the staged object bytes (the device already holds
+//                   them); false leaves the data part to the caller (mec_encode_sg: the writer emits the digest followed
+//                   by the slice of its own source buffer, as streamingBitrotWriter.Write does — no copy anywhere)
+static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* files, bool with_data, uint8_t* data_digests) {
+  Slot& s = *ch.s;
+  const int k = c->k, m = c->m, n = c->n;
+  const int64_t bs = c->block_size, S = c->S(), fstride = 32 + S;
+  int rc;
+  if ((rc = s.hdig.ensure(static_cast<size_t>(ch.nb * n * 32)))) return rc;
+  MEC_CUDA_OK(cudaMemcpyAsync(s.hdig.p, s.dig.p, static_cast<size_t>(ch.nb * n * 32), cudaMemcpyDeviceToHost, s.st));
+  const int64_t per_t = ch.tail > 0 ? ceil_frac(ch.tail, k) : 0;
+  for (int j = 0; j < m; j++) {
+    uint8_t* f = files[k + j];
+    if (!f) continue;
+    f += ch.b0 * fstride + 32;
+    if (ch.nfull > 0)
+      MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), static_cast<uint8_t*>(s.out.p) + j * ch.pitch,
+                                    static_cast<size_t>(m * ch.pitch), static_cast<size_t>(S), static_cast<size_t>(ch.nfull),
+                                    cudaMemcpyDeviceToHost, s.st));
+    if (ch.tail > 0)
+      MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, static_cast<uint8_t*>(s.out.p) + (ch.nfull * m + j) * ch.pitch,
+                                  static_cast<size_t>(per_t), cudaMemcpyDeviceToHost, s.st));
+    c->st_d2h += ch.nfull * S + per_t;
+  }
+  if (with_data) {
+    for (int i = 0; i < k; i++) {
+      uint8_t* f = files[i];
+      if (!f) continue;
+      f += ch.b0 * fstride + 32;
+      const int64_t w = std::max<int64_t>(0, std::min(S, bs - static_cast<int64_t>(i) * S));  // Split: the last shard is short, the rest is zero padding
+      if (ch.nfull > 0 && w > 0)
+        MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), static_cast<const uint8_t*>(s.src.p) + static_cast<int64_t>(i) * S,
+                                      static_cast<size_t>(bs), static_cast<size_t>(w), static_cast<size_t>(ch.nfull), cudaMemcpyDeviceToHost, s.st));
+      if (ch.tail > 0) {
+        const int64_t start = static_cast<int64_t>(i) * per_t, have = std::max<int64_t>(0, std::min(per_t, ch.tail - start));
+        if (have > 0)
+          MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, static_cast<const uint8_t*>(s.src.p) + ch.nfull * bs + start,
+                                      static_cast<size_t>(have), cudaMemcpyDeviceToHost, s.st));
+      }
+      c->st_d2h += ch.nfull * w;
+    }
+  }
+  (void)data_digests;
+  return MEC_OK;
+}
+
+static void frames_retire(mec_codec* c, const EncChunk& ch, uint8_t* const* files, bool with_data, uint8_t* data_digests) {
+  const int k = c->k, n = c->n;
+  const int64_t bs = c->block_size, S = c->S(), fstride = 32 + S;
+  const uint8_t* hd = static_cast<const uint8_t*>(ch.s->hdig.p);
+  const int64_t per_t = ch.tail > 0 ? ceil_frac(ch.tail, k) : 0;
+  for (int64_t b = 0; b < ch.nb; b++) {
+    const bool is_tail = b >= ch.nfull;
+    for (int i = 0; i < n; i++) {
+      const uint8_t* dg = hd + (b * n + i) * 32;
+      if (data_digests && i < k) memcpy(data_digests + ((ch.b0 + b) * k + i) * 32, dg, 32);
+      uint8_t* f = files ? files[i] : nullptr;
+      if (!f || (i < k && !with_data)) continue;
+      f += (ch.b0 + b) * fstride;
+      memcpy(f, dg, 32);  // hash first, then the shard (cmd/bitrot-streaming.go:60,65)
+      if (i < k) {        // Split's zero padding behind the object bytes (cmd/erasure-coding.go:81)
+        const int64_t per = is_tail ? per_t : S, blen = is_tail ? ch.tail : bs;
+        const int64_t have = std::max<int64_t>(0, std::min(per, blen - static_cast<int64_t>(i) * per));
+        if (have < per) memset(f + 32 + have, 0, static_cast<size_t>(per - have));
+      }
+    }
+  }
+}
+
+static int64_t encode_frames(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, bool with_data,
+                             uint8_t* data_digests, int write_quorum, const char* what) {
+  NvtxRange nvtx(what);
   if (!c || len < 0 || !files) return MEC_ERR_INVALID_ARGUMENT;
   int online = 0;
   for (int i = 0; i < c->n; i++) online += files[i] != nullptr;
@@ -306,30 +433,27 @@ extern "C" int64_t mec_encode(mec_codec* c, const uint8_t* src, int64_t len, uin
   if (len == 0) return 0;
   int rc = require_streaming(c);
   if (rc) return rc;
-  const int64_t bs = c->block_size, S = c->S(), nall = ceil_frac(len, bs);
-  std::vector<uint8_t> parity(static_cast<size_t>(nall * std::max(c->m, 1) * S));
-  std::vector<uint8_t> dig(static_cast<size_t>(nall * c->n * 32));
-  rc = mec_encode_blocks(c, src, len, parity.data(), dig.data());
-  if (rc) return rc;
-  std::vector<int64_t> pos(c->n, 0);
-  for (int64_t b = 0; b < nall; b++) {
-    const int64_t blen = std::min(bs, len - b * bs), per = ceil_frac(blen, c->k);
-    for (int i = 0; i < c->n; i++) {
-      if (!files[i]) continue;
-      uint8_t* f = files[i] + pos[i];
-      memcpy(f, dig.data() + (b * c->n + i) * 32, 32);  // hash first, then the shard (bitrot-streaming.go:60,65)
-      if (i < c->k) {
-        const int64_t start = static_cast<int64_t>(i) * per;
-        const int64_t have = std::max<int64_t>(0, std::min(per, blen - start));
-        if (have > 0) memcpy(f + 32, src + b * bs + start, static_cast<size_t>(have));
-        if (have < per) memset(f + 32 + have, 0, static_cast<size_t>(per - have));
-      } else {
-        memcpy(f + 32, parity.data() + (b * c->m + (i - c->k)) * S, static_cast<size_t>(per));
-      }
-      pos[i] += 32 + per;
-    }
-  }
-  return len;
+  if (c->S() >= (1ll << 31)) return MEC_ERR_UNSUPPORTED;
+  std::lock_guard<std::mutex> lk(c->mu);
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  rc = encode_pipeline(
+      c, src, len, [&](const EncChunk& ch) -> int { return frames_enqueue(c, ch, files, with_data, data_digests); },
+      [&](const EncChunk& ch) { frames_retire(c, ch, files, with_data, data_digests); });
+  return rc ? rc : len;
+}
+
+// Erasure.Encode + streaming bitrot writers (cmd/erasure-encode.go:69, cmd/bitrot-streaming.go:44-75): complete part.N images.
+extern "C" int64_t mec_encode(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, int write_quorum) {
+  return encode_frames(c, src, len, files, true, nullptr, write_quorum, "mec_encode");
+}
+
+// Scatter-gather form of the same call: the k data shards stay where Split left them — inside `src` — and only what the GPU
+// produced comes back: complete frames for the parity drives (files[k..n), NULL = offline) and the digests of the data shards
+// ([block][k][32]).  files[0..k) are only tested for NULL (offline writers count against the quorum).
+extern "C" int64_t mec_encode_sg(mec_codec* c, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* data_digests,
+                                 int write_quorum) {
+  if (!data_digests) return MEC_ERR_INVALID_ARGUMENT;
+  return encode_frames(c, src, len, files, false, data_digests, write_quorum, "mec_encode_sg");
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,147 +478,276 @@ static int stage_frames(const uint8_t* host, void* dev, const FrameGeom& g, cuda
   return MEC_OK;
 }
 
-// Rebuild shards `targets` for blocks [0, g.nblocks) from the staged survivor files chosen[0..k).
-// d_out rows: (b*r + q); digests [b][k + r]; flags [b][k].
-static int launch_reconstruct(mec_codec* c, const FrameGeom& g, int64_t cur, const int* chosen, int r,
-                              const uint8_t* rows, uint8_t* d_out, int64_t pitch, uint8_t* d_dig, uint8_t* d_flags,
-                              cudaStream_t st, bool hash_outputs) {
+// Where the rebuilt / read shards of a range go.
+//   frame sink  (Heal, mec_reconstruct_frames): out[i] = frame-layout image of shard i, same geometry as the inputs
+//   object sink (Decode): the data shards of every block, cut to the object bytes [lo, hi) and laid end to end in dst —
+//                writeDataBlocks (cmd/erasure-utils.go:42) done by the copy engines: one 2-D copy per data shard and chunk
+struct RangeSink {
+  uint8_t* const* out = nullptr;
+  uint8_t* dst = nullptr;
+  int64_t first_block = 0;   // index (within the part) of the range's first block
+  int64_t lo = 0, hi = 0;    // wanted part bytes
+  int64_t bs = 0, total = 0; // block size, part size
+};
+
+// One chunk of the reconstruct pipeline: blocks [b0, b0 + nb) of the range, read through reader set `chosen`.
+struct RChunk {
+  int64_t b0 = 0, nb = 0;
+  int chosen[kMaxK];
+  int targets[kMaxR];
+  int r = 0;
+  uint64_t epoch = 0;  // reader-set generation the chunk was submitted under
+};
+
+// survivors of a chunk sit in ONE arena per slot at a uniform stride (position t of the reader set at t * stride)
+static inline uint8_t* arena_ptr(Slot& s, int64_t stride, int t) { return static_cast<uint8_t*>(s.aux.p) + t * stride; }
+
+// Rebuild `ch.targets` for the chunk from the staged survivor frames.  d_out rows: (b*r + q); digests [b][k + r]; flags [b][k].
+static int launch_reconstruct(mec_codec* c, const FrameGeom& g, const RChunk& ch, Slot& s, int64_t stride, const uint8_t* rows,
+                              int64_t pitch, bool hash_outputs) {
+  const int k = c->k, r = ch.r;
   FusedDesc d;
-  d.k = c->k; d.r = r; d.coef = rows; d.static_encode = false; d.contiguous = false; d.hash_outputs = hash_outputs;
+  d.k = k; d.r = r; d.coef = rows; d.static_encode = false; d.contiguous = false; d.hash_outputs = hash_outputs;
   d.key = kMagicKey; d.out_pitch = pitch; d.expect_block_stride = g.dpitch(); d.in_block_stride = g.dpitch();
-  // blocks [cur, g.nblocks) of the staged files; outputs are indexed from block `cur`
-  const int64_t nfull_all = (g.last_len == g.S) ? g.nblocks : g.nblocks - 1;
+  // the range's short last block (if this chunk holds it) is a second launch with its own shard length
+  const bool has_short = (ch.b0 + ch.nb == g.nblocks) && g.last_len != g.S;
+  const int64_t nfull = has_short ? ch.nb - 1 : ch.nb;
   for (int pass = 0; pass < 2; pass++) {
-    const int64_t first = pass == 0 ? cur : std::max(cur, nfull_all);
-    const int64_t nb = pass == 0 ? nfull_all - cur : g.nblocks - std::max(cur, nfull_all);
+    const int64_t first = pass == 0 ? 0 : nfull;
+    const int64_t nb = pass == 0 ? nfull : ch.nb - nfull;
     if (nb <= 0) continue;
     d.nblocks = nb;
     d.S = static_cast<int32_t>(pass == 0 ? g.S : g.last_len);
-    for (int t = 0; t < c->k; t++) {
-      const uint8_t* base = static_cast<const uint8_t*>(c->in_files[chosen[t]].p);
-      d.map_base[t] = base + first * g.dpitch();
-      d.map_len[t] = g.dev_bytes() - first * g.dpitch();
-      d.expect_ptr[t] = base + first * g.dpitch();
-      d.in_ptr[t] = base + first * g.dpitch() + 32;
+    for (int t = 0; t < k; t++) {
+      const uint8_t* base = arena_ptr(s, stride, t) + first * g.dpitch();
+      d.map_base[t] = base;
+      d.map_len[t] = stride - first * g.dpitch();
+      d.expect_ptr[t] = base;
+      d.in_ptr[t] = base + 32;
     }
-    d.out = d_out + (first - cur) * r * pitch;
-    d.digests = d_dig + (first - cur) * (c->k + r) * 32;
-    d.corrupt = d_flags + (first - cur) * c->k;
-    int rc = c->eng->launch_fused(d, c->opt, st);
+    d.out = static_cast<uint8_t*>(s.out.p) + first * r * pitch;
+    d.digests = static_cast<uint8_t*>(s.dig.p) + first * (k + r) * 32;
+    d.corrupt = static_cast<uint8_t*>(s.flags.p) + first * k;
+    int rc = c->eng->launch_fused(d, c->opt, s.st);
     if (rc) return rc;
   }
   return MEC_OK;
 }
 
-// Core of Decode/Heal: frames[i] point at the first frame of the range (host), out[i] likewise.
+// parallelReader.Read's choice of readers (cmd/erasure-decode.go:145-221): the first k alive readers in index order,
+// preferred ones first (preferReaders, :92-123)
+static int choose_readers(const mec_codec* c, const uint8_t* const* frames, const uint8_t* alive, const uint8_t* prefer, int* chosen) {
+  const int k = c->k, n = c->n;
+  int nch = 0;
+  if (prefer) {
+    int order[kMaxShards], next = 0;
+    for (int i = 0; i < n; i++) order[i] = i;
+    for (int i = 0; i < n; i++) {
+      if (!prefer[i] || frames[i] == nullptr) continue;
+      if (i == next) { next++; continue; }
+      std::swap(order[next], order[i]);
+      next++;
+    }
+    for (int q = 0; q < n && nch < k; q++)
+      if (alive[order[q]]) chosen[nch++] = order[q];
+    std::sort(chosen, chosen + nch);  // decode rows are defined on ascending shard indices
+  } else {
+    for (int i = 0; i < n && nch < k; i++)
+      if (alive[i]) chosen[nch++] = i;
+  }
+  return nch;
+}
+
+// device->host copies of one verified-or-not chunk into the object sink (optimistic: a chunk that turns out to hold a corrupt
+// frame is redone from the bad block with other readers and its bytes are overwritten before the call returns)
+static int emit_object(mec_codec* c, const FrameGeom& g, const RangeSink& sk, const RChunk& ch, Slot& s, int64_t stride, int64_t pitch) {
+  const int k = c->k, r = ch.r;
+  const int64_t bs = sk.bs, S = g.S, P = g.dpitch();
+  for (int i = 0; i < k; i++) {
+    // device source of data shard i: a staged survivor frame or a rebuilt row
+    const uint8_t* base = nullptr;
+    int64_t spitch = 0;
+    for (int t = 0; t < k && !base; t++)
+      if (ch.chosen[t] == i) { base = arena_ptr(s, stride, t) + 32; spitch = P; }
+    for (int q = 0; q < r && !base; q++)
+      if (ch.targets[q] == i) { base = static_cast<uint8_t*>(s.out.p) + q * pitch; spitch = r * pitch; }
+    if (!base) return MEC_ERR_UNEXPECTED;
+    // blocks of the chunk: a run of blocks that are wanted in full goes out as one 2-D copy, partial ones one by one
+    int64_t run0 = -1;
+    auto flush = [&](int64_t run1) -> int {  // blocks [run0, run1) of the chunk, all full and fully wanted
+      if (run0 < 0 || run1 <= run0) { run0 = -1; return MEC_OK; }
+      const int64_t w = std::max<int64_t>(0, std::min(S, bs - static_cast<int64_t>(i) * S));
+      if (w > 0) {
+        const int64_t B = sk.first_block + ch.b0 + run0;
+        MEC_CUDA_OK(cudaMemcpy2DAsync(sk.dst + (B * bs + static_cast<int64_t>(i) * S - sk.lo), static_cast<size_t>(bs), base + run0 * spitch,
+                                      static_cast<size_t>(spitch), static_cast<size_t>(w), static_cast<size_t>(run1 - run0), cudaMemcpyDeviceToHost, s.st));
+        c->st_d2h += w * (run1 - run0);
+      }
+      run0 = -1;
+      return MEC_OK;
+    };
+    int rc;
+    for (int64_t b = 0; b < ch.nb; b++) {
+      const int64_t B = sk.first_block + ch.b0 + b;
+      const int64_t blo = B * bs, bhi = std::min(blo + bs, sk.total);          // part bytes of this block
+      const int64_t cur = (ch.b0 + b == g.nblocks - 1) ? g.last_len : S;       // its shard length
+      const bool whole = blo >= sk.lo && bhi <= sk.hi && bhi - blo == bs && cur == S;
+      if (whole) { if (run0 < 0) run0 = b; continue; }
+      if ((rc = flush(b))) return rc;
+      const int64_t slo = blo + static_cast<int64_t>(i) * cur, shi = std::min(slo + cur, bhi);
+      const int64_t a = std::max(slo, sk.lo), e = std::min(shi, sk.hi);
+      if (e > a) {
+        MEC_CUDA_OK(cudaMemcpyAsync(sk.dst + (a - sk.lo), base + b * spitch + (a - slo), static_cast<size_t>(e - a), cudaMemcpyDeviceToHost, s.st));
+        c->st_d2h += e - a;
+      }
+    }
+    if ((rc = flush(ch.nb))) return rc;
+  }
+  return MEC_OK;
+}
+
+// rebuilt shards of a chunk -> frame-layout outputs (digest + shard per block)
+static int emit_frames(mec_codec* c, const FrameGeom& g, const RangeSink& sk, const RChunk& ch, Slot& s, int64_t pitch) {
+  const int k = c->k, r = ch.r;
+  const int64_t fstride = 32 + g.S;
+  const bool has_short = (ch.b0 + ch.nb == g.nblocks) && g.last_len != g.S;
+  const int64_t nfull = has_short ? ch.nb - 1 : ch.nb;
+  for (int q = 0; q < r; q++) {
+    uint8_t* dst = sk.out[ch.targets[q]];
+    if (!dst) continue;
+    dst += ch.b0 * fstride;
+    if (nfull > 0) {
+      MEC_CUDA_OK(cudaMemcpy2DAsync(dst, static_cast<size_t>(fstride), static_cast<uint8_t*>(s.dig.p) + (k + q) * 32,
+                                    static_cast<size_t>((k + r) * 32), 32, static_cast<size_t>(nfull), cudaMemcpyDeviceToHost, s.st));
+      MEC_CUDA_OK(cudaMemcpy2DAsync(dst + 32, static_cast<size_t>(fstride), static_cast<uint8_t*>(s.out.p) + q * pitch,
+                                    static_cast<size_t>(r * pitch), static_cast<size_t>(g.S), static_cast<size_t>(nfull), cudaMemcpyDeviceToHost, s.st));
+    }
+    if (has_short) {
+      const int64_t b = nfull;
+      MEC_CUDA_OK(cudaMemcpyAsync(dst + b * fstride, static_cast<uint8_t*>(s.dig.p) + (b * (k + r) + k + q) * 32, 32, cudaMemcpyDeviceToHost, s.st));
+      MEC_CUDA_OK(cudaMemcpyAsync(dst + b * fstride + 32, static_cast<uint8_t*>(s.out.p) + (b * r + q) * pitch, static_cast<size_t>(g.last_len),
+                                  cudaMemcpyDeviceToHost, s.st));
+    }
+    c->st_d2h += nfull * (32 + g.S) + (has_short ? 32 + g.last_len : 0);
+  }
+  return MEC_OK;
+}
+
+// Core of Decode / Heal: frames[i] point at the first frame of the range (host).  The range is cut into chunks that run through
+// the codec's three slots — while chunk c is in the kernel, chunk c+1 is being staged and chunk c-1 is on its way back — each
+// slot with its own stream, survivor arena, output and flag buffers.  Chunks retire in order: the per-frame digest verdicts
+// ([block][reader] flags written by the hash threads) are read, and on the first mismatch the failing readers are dropped
+// for the rest of the call (parallelReader.Read: p.readers[i] = nil, cmd/erasure-decode.go:196-199), everything submitted
+// behind the bad block is discarded and the range resumes AT the bad block with the next readers in order — exactly the
+// block-sequential fail-over of the reference, without giving up the pipelining in the common clean case.
 static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const FrameGeom& g, const uint8_t* want,
-                             int data_only, uint8_t* const* out, uint8_t* corrupt, uint8_t* alive /*n, in/out*/,
+                             int data_only, const RangeSink& sk, uint8_t* corrupt, uint8_t* alive /*n, in/out*/,
                              const uint8_t* prefer = nullptr, bool hash_outputs = true) {
   NvtxRange nvtx("mec_reconstruct_range");
   const int k = c->k, n = c->n;
+  if (k > kMaxK) return MEC_ERR_UNSUPPORTED;
   MEC_CUDA_OK(cudaSetDevice(c->device));
-  cudaStream_t st = c->slots[0].st;
-  const int64_t fstride = 32 + g.S;
-  std::vector<char> staged(n, 0);
-  int64_t cur = 0;
-  while (cur < g.nblocks) {
-    // parallelReader.Read: first k alive readers in index order (cmd/erasure-decode.go:145-221)
-    int chosen[kMaxShards], nch = 0;
-    if (prefer) {  // preferReaders (cmd/erasure-decode.go:92-123): preferred readers are swapped to the front
-      int order[kMaxShards], next = 0;
-      for (int i = 0; i < n; i++) order[i] = i;
-      for (int i = 0; i < n; i++) {
-        if (!prefer[i] || frames[i] == nullptr) continue;
-        if (i == next) { next++; continue; }
-        std::swap(order[next], order[i]);
-        next++;
-      }
-      for (int q = 0; q < n && nch < k; q++)
-        if (alive[order[q]]) chosen[nch++] = order[q];
-      std::sort(chosen, chosen + nch);  // decode rows are defined on ascending shard indices
-    } else {
-      for (int i = 0; i < n && nch < k; i++)
-        if (alive[i]) chosen[nch++] = i;
-    }
-    if (nch < k) return MEC_ERR_READ_QUORUM;
+  struct Drain {
+    mec_codec* c;
+    ~Drain() { for (auto& s : c->slots) if (s.st) cudaStreamSynchronize(s.st); }
+  } drain{c};
+  const int64_t fstride = 32 + g.S, P = g.dpitch(), pitch = round_up(g.S, 16);
+  int64_t chunk = c->opt.chunk_blocks > 0 ? c->opt.chunk_blocks : std::max<int64_t>(1, (32ll << 20) / std::max<int64_t>(1, g.S * k));
+  chunk = std::min(chunk, g.nblocks);
+  const int64_t stride = round_up(chunk * P + 512, 256);
+
+  RChunk inflight[kSlots];
+  std::vector<uint8_t> rows_of[kSlots];
+  bool busy[kSlots] = {};
+  int head = 0, tail = 0, nbusy = 0;  // ring: tail = oldest in flight, head = next free slot
+  int64_t next = 0, done = 0;         // next block to submit, blocks accepted so far
+  uint64_t epoch = 0;
+  int rc;
+
+  auto submit = [&](int si, int64_t b0) -> int {
+    Slot& s = c->slots[si];
+    RChunk& ch = inflight[si];
+    ch.b0 = b0; ch.nb = std::min(chunk, g.nblocks - b0); ch.epoch = epoch;
+    if (choose_readers(c, frames, alive, prefer, ch.chosen) < k) return MEC_ERR_READ_QUORUM;
     std::vector<uint8_t> present(n, 0);
-    for (int t = 0; t < k; t++) present[chosen[t]] = 1;
-    int targets[kMaxShards], r = 0;
+    for (int t = 0; t < k; t++) present[ch.chosen[t]] = 1;
+    ch.r = 0;
     for (int i = 0; i < n; i++)
-      if (want[i] && !present[i] && !(data_only && i >= k)) targets[r++] = i;
-    if (r > kMaxR || k > kMaxK) return MEC_ERR_UNSUPPORTED;
-    std::vector<uint8_t> rows(static_cast<size_t>(std::max(r, 1)) * k);
+      if (want[i] && !present[i] && !(data_only && i >= k)) {
+        if (ch.r >= kMaxR) return MEC_ERR_UNSUPPORTED;
+        ch.targets[ch.r++] = i;
+      }
+    rows_of[si].assign(static_cast<size_t>(std::max(ch.r, 1)) * k, 0);
     int valid[kMaxShards];
-    if (r > 0 && !rs_decode_rows(k, c->m, present.data(), targets, r, rows.data(), valid)) return MEC_ERR_TOO_FEW_SHARDS;
-    // stage survivors (whole range once per file)
-    int rc;
+    if (ch.r > 0 && !rs_decode_rows(k, c->m, present.data(), ch.targets, ch.r, rows_of[si].data(), valid)) return MEC_ERR_TOO_FEW_SHARDS;
+    int e;
+    if ((e = s.aux.ensure(static_cast<size_t>(k * stride)))) return e;
+    if ((e = s.out.ensure(static_cast<size_t>(ch.nb * std::max(ch.r, 1) * pitch)))) return e;
+    if ((e = s.dig.ensure(static_cast<size_t>(ch.nb * (k + ch.r) * 32)))) return e;
+    if ((e = s.flags.ensure(static_cast<size_t>(ch.nb * k)))) return e;
+    if ((e = s.hflags.ensure(static_cast<size_t>(ch.nb * k)))) return e;
+    FrameGeom sub = g;  // geometry of the chunk: its last block is short only if it is the range's last block
+    sub.nblocks = ch.nb;
+    sub.last_len = (b0 + ch.nb == g.nblocks) ? g.last_len : g.S;
     for (int t = 0; t < k; t++) {
-      const int i = chosen[t];
-      if (staged[i]) continue;
-      if ((rc = c->in_files[i].ensure(static_cast<size_t>(g.dev_bytes())))) return rc;
-      if ((rc = stage_frames(frames[i], c->in_files[i].p, g, st))) return rc;
-      staged[i] = 1;
+      if ((e = stage_frames(frames[ch.chosen[t]] + b0 * fstride, arena_ptr(s, stride, t), sub, s.st))) return e;
+      c->st_h2d += sub.file_bytes();
     }
-    FrameGeom sub = g;
-    sub.nblocks = g.nblocks - cur;
-    const int64_t pitch = round_up(g.S, 16);
-    Slot& s = c->slots[0];
-    if ((rc = s.out.ensure(static_cast<size_t>(sub.nblocks * std::max(r, 1) * pitch)))) return rc;
-    if ((rc = s.dig.ensure(static_cast<size_t>(sub.nblocks * (k + r) * 32)))) return rc;
-    if ((rc = c->flags.ensure(static_cast<size_t>(sub.nblocks * k)))) return rc;
-    MEC_CUDA_OK(cudaMemsetAsync(c->flags.p, 0, static_cast<size_t>(sub.nblocks * k), st));
-    rc = launch_reconstruct(c, g, cur, chosen, r, rows.data(), static_cast<uint8_t*>(s.out.p), pitch,
-                            static_cast<uint8_t*>(s.dig.p), static_cast<uint8_t*>(c->flags.p), st, hash_outputs);
-    if (rc) return rc;
-    std::vector<uint8_t> flags(static_cast<size_t>(sub.nblocks * k));
-    MEC_CUDA_OK(cudaMemcpyAsync(flags.data(), c->flags.p, flags.size(), cudaMemcpyDeviceToHost, st));
-    MEC_CUDA_OK(cudaStreamSynchronize(st));
-    // earliest block with a digest mismatch among the chosen readers
-    int64_t bad = sub.nblocks;
-    for (int64_t b = 0; b < sub.nblocks && bad == sub.nblocks; b++)
+    MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(ch.nb * k), s.st));
+    if ((e = launch_reconstruct(c, g, ch, s, stride, rows_of[si].data(), pitch, hash_outputs))) return e;
+    MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(ch.nb * k), cudaMemcpyDeviceToHost, s.st));
+    if (sk.dst) { if ((e = emit_object(c, g, sk, ch, s, stride, pitch))) return e; }
+    else if (sk.out) { if ((e = emit_frames(c, g, sk, ch, s, pitch))) return e; }
+    return MEC_OK;
+  };
+
+  while (done < g.nblocks) {
+    while (nbusy < kSlots && next < g.nblocks) {
+      if ((rc = submit(head, next))) return rc;
+      next += inflight[head].nb;
+      busy[head] = true;
+      head = (head + 1) % kSlots;
+      nbusy++;
+    }
+    // retire the oldest chunk
+    const int si = tail;
+    Slot& s = c->slots[si];
+    RChunk& ch = inflight[si];
+    MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+    busy[si] = false;
+    tail = (tail + 1) % kSlots;
+    nbusy--;
+    const uint8_t* fl = static_cast<const uint8_t*>(s.hflags.p);
+    int64_t bad = ch.nb;
+    for (int64_t b = 0; b < ch.nb && bad == ch.nb; b++)
       for (int t = 0; t < k; t++)
-        if (flags[static_cast<size_t>(b * k + t)]) { bad = b; break; }
-    const int64_t good = bad;  // blocks [cur, cur+good) are accepted
-    if (good > 0) {
-      const int64_t nfull = (cur + good == g.nblocks && g.last_len != g.S) ? good - 1 : good;
-      for (int q = 0; q < r; q++) {
-        uint8_t* dst = out[targets[q]];
-        if (!dst) continue;
-        dst += cur * fstride;
-        if (nfull > 0) {
-          MEC_CUDA_OK(cudaMemcpy2DAsync(dst, static_cast<size_t>(fstride), static_cast<uint8_t*>(s.dig.p) + (k + q) * 32,
-                                        static_cast<size_t>((k + r) * 32), 32, static_cast<size_t>(nfull), cudaMemcpyDeviceToHost, st));
-          MEC_CUDA_OK(cudaMemcpy2DAsync(dst + 32, static_cast<size_t>(fstride), static_cast<uint8_t*>(s.out.p) + q * pitch,
-                                        static_cast<size_t>(r * pitch), static_cast<size_t>(g.S), static_cast<size_t>(nfull),
-                                        cudaMemcpyDeviceToHost, st));
-        }
-        if (nfull < good) {  // the short last block
-          const int64_t b = good - 1;
-          MEC_CUDA_OK(cudaMemcpyAsync(dst + b * fstride, static_cast<uint8_t*>(s.dig.p) + (b * (k + r) + k + q) * 32, 32,
-                                      cudaMemcpyDeviceToHost, st));
-          MEC_CUDA_OK(cudaMemcpyAsync(dst + b * fstride + 32, static_cast<uint8_t*>(s.out.p) + (b * r + q) * pitch,
-                                      static_cast<size_t>(g.last_len), cudaMemcpyDeviceToHost, st));
-        }
-      }
-      // wanted shards that were read (present) are passed through unchanged
+        if (fl[b * k + t]) { bad = b; break; }
+    const int64_t good = bad;  // blocks [b0, b0 + good) are accepted
+    if (good > 0 && sk.out) {  // wanted shards that were read are passed through unchanged
+      std::vector<uint8_t> present(n, 0);
+      for (int t = 0; t < k; t++) present[ch.chosen[t]] = 1;
       for (int i = 0; i < n; i++) {
-        if (!want[i] || !present[i] || !out[i] || out[i] == frames[i]) continue;
-        const int64_t bytes = (cur + good == g.nblocks) ? (g.file_bytes() - cur * fstride) : good * fstride;
-        memcpy(out[i] + cur * fstride, frames[i] + cur * fstride, static_cast<size_t>(bytes));
+        if (!want[i] || !present[i] || !sk.out[i] || sk.out[i] == frames[i]) continue;
+        const int64_t bytes = (ch.b0 + good == g.nblocks) ? (g.file_bytes() - ch.b0 * fstride) : good * fstride;
+        memcpy(sk.out[i] + ch.b0 * fstride, frames[i] + ch.b0 * fstride, static_cast<size_t>(bytes));
       }
-      MEC_CUDA_OK(cudaStreamSynchronize(st));
-    }
-    if (bad < sub.nblocks) {  // drop every chosen reader that failed at block `bad`, retry from there
-      for (int t = 0; t < k; t++)
-        if (flags[static_cast<size_t>(bad * k + t)]) {
-          alive[chosen[t]] = 0;
-          if (corrupt) corrupt[chosen[t]] = 1;
-          c->st_corrupt++;
-        }
     }
     c->st_blocks_read += good;
-    c->st_shards_rebuilt += good * r;
-    cur += good;
+    c->st_shards_rebuilt += good * ch.r;
+    done = ch.b0 + good;
+    if (bad < ch.nb) {  // drop every chosen reader that failed at block `bad`, resume there with the next readers
+      for (int t = 0; t < k; t++)
+        if (fl[bad * k + t]) {
+          if (alive[ch.chosen[t]]) c->st_corrupt++;
+          alive[ch.chosen[t]] = 0;
+          if (corrupt) corrupt[ch.chosen[t]] = 1;
+        }
+      for (int q = 0; q < kSlots; q++)  // whatever was submitted behind it ran with the old reader set: discard
+        if (busy[q]) { MEC_CUDA_OK(cudaStreamSynchronize(c->slots[q].st)); busy[q] = false; }
+      head = tail = 0; nbusy = 0;
+      next = done;
+      epoch++;
+    }
   }
   return MEC_OK;
 }
@@ -555,7 +808,9 @@ extern "C" int mec_reconstruct_frames(mec_codec* c, const uint8_t* const* frames
   if (g.last_len > g.S) return MEC_ERR_INVALID_ARGUMENT;
   std::vector<uint8_t> alive(c->n);
   for (int i = 0; i < c->n; i++) alive[i] = frames[i] != nullptr;
-  return reconstruct_range(c, frames, g, want, data_only, out, corrupt, alive.data());
+  RangeSink sk;
+  sk.out = out;
+  return reconstruct_range(c, frames, g, want, data_only, sk, corrupt, alive.data());
 }
 
 extern "C" int64_t mec_decode(mec_codec* c, const uint8_t* const* files, int64_t offset, int64_t length,
@@ -571,6 +826,7 @@ extern "C" int64_t mec_decode_prefer(mec_codec* c, const uint8_t* const* files, 
   if (offset < 0 || length < 0) return MEC_ERR_INVALID_ARGUMENT;      // cmd/erasure-decode.go:240-242
   if (offset + length > total) return MEC_ERR_INVALID_ARGUMENT;       // :243-245
   if (length == 0) return 0;                                          // :247-249
+  if (!dst) return MEC_ERR_INVALID_ARGUMENT;
   int rc = require_streaming(c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
@@ -586,46 +842,33 @@ extern "C" int64_t mec_decode_prefer(mec_codec* c, const uint8_t* const* files, 
   g.nblocks = last_block - start_block + 1;
   g.S = S;
   g.last_len = std::min(S, sfs - last_block * S);
+  // writeDataBlocks (cmd/erasure-utils.go:42): a block whose k shards hold fewer bytes than asked of it is ErrShortData
+  // (every block but the part's last holds k*S >= block_size bytes, so only that one can fall short)
+  if (static_cast<int64_t>(k) * g.last_len < std::min(offset + length, total) - last_block * bs) return MEC_ERR_SHORT_DATA;
   const int64_t fstride = 32 + S, foff = start_block * fstride;
   std::vector<const uint8_t*> in(n);
   std::vector<uint8_t> alive(n), want(n, 0), corrupt(n, 0);
   for (int i = 0; i < n; i++) { in[i] = files[i] ? files[i] + foff : nullptr; alive[i] = files[i] != nullptr; }
   for (int i = 0; i < k; i++) want[i] = 1;
-  std::vector<std::vector<uint8_t>> tmp(k);
-  std::vector<uint8_t*> out(n, nullptr);
-  for (int i = 0; i < k; i++) { tmp[i].resize(static_cast<size_t>(g.file_bytes())); out[i] = tmp[i].data(); }
+  RangeSink sk;
+  sk.dst = dst; sk.first_block = start_block; sk.lo = offset; sk.hi = offset + length; sk.bs = bs; sk.total = total;
   // GetObject only consumes the data bytes of the rebuilt shards: their digests are not computed
-  rc = reconstruct_range(c, in.data(), g, want.data(), 1, out.data(), corrupt.data(), alive.data(), prefer, false);
+  rc = reconstruct_range(c, in.data(), g, want.data(), 1, sk, corrupt.data(), alive.data(), prefer, false);
   if (rc) return rc;
-  // writeDataBlocks (cmd/erasure-utils.go:42) per block
-  int64_t written = 0;
-  for (int64_t block = start_block; block <= last_block; block++) {
-    int64_t bo, bl;
-    if (start_block == end_block) { bo = offset % bs; bl = length; }
-    else if (block == start_block) { bo = offset % bs; bl = bs - bo; }
-    else if (block == end_block) { bo = 0; bl = (offset + length) % bs; }
-    else { bo = 0; bl = bs; }
-    if (bl == 0) break;
-    const int64_t cur = (block == last_block) ? g.last_len : S;
-    if (static_cast<int64_t>(k) * cur < bl) return MEC_ERR_SHORT_DATA;
-    int64_t o = bo, w = bl;
-    for (int i = 0; i < k && w > 0; i++) {
-      if (o >= cur) { o -= cur; continue; }
-      const int64_t take = std::min(cur - o, w);
-      memcpy(dst + written, tmp[i].data() + (block - start_block) * fstride + 32 + o, static_cast<size_t>(take));
-      written += take; w -= take; o = 0;
-    }
-  }
-  if (written != length) return MEC_ERR_LESS_DATA;
   if (heal_hint)
     for (int i = 0; i < n; i++)
       if (corrupt[i]) *heal_hint = MEC_ERR_FILE_CORRUPT;
-  return written;
+  return length;
 }
 
-extern "C" int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total, uint8_t* const* out_files) {
+// Erasure.Heal (cmd/erasure-decode.go:317).  Like the reference it reports bitrot met on the way: when a source reader failed
+// its digest the stale shards are still rebuilt from the others and written, and the call returns MEC_ERR_FILE_CORRUPT
+// (Heal's `derr`, :338-341,366 — healObject aborts the part on it, cmd/erasure-healing.go:603-608); corrupt[i] names the readers.
+extern "C" int mec_heal_prefer(mec_codec* c, const uint8_t* const* files, const uint8_t* prefer, int64_t total,
+                               uint8_t* const* out_files, uint8_t* corrupt) {
   NvtxRange nvtx("mec_heal");
   if (!c || !files || !out_files) return MEC_ERR_INVALID_ARGUMENT;
+  if (corrupt) memset(corrupt, 0, static_cast<size_t>(c->n));
   int rc = require_streaming(c);
   if (rc) return rc;
   if (total <= 0) return MEC_OK;
@@ -636,14 +879,25 @@ extern "C" int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total
   g.nblocks = ceil_frac(total, c->block_size);
   g.S = S;
   g.last_len = sfs - (g.nblocks - 1) * S;
-  std::vector<uint8_t> alive(n), want(n, 0);
+  std::vector<uint8_t> alive(n), want(n, 0), bad(n, 0);
   for (int i = 0; i < n; i++) { alive[i] = files[i] != nullptr; want[i] = out_files[i] != nullptr; }
-  return reconstruct_range(c, files, g, want.data(), 0, out_files, nullptr, alive.data());
+  RangeSink sk;
+  sk.out = out_files;
+  rc = reconstruct_range(c, files, g, want.data(), 0, sk, bad.data(), alive.data(), prefer);
+  if (rc) return rc;
+  bool any = false;
+  for (int i = 0; i < n; i++) { any |= bad[i] != 0; if (corrupt) corrupt[i] = bad[i]; }
+  return any ? MEC_ERR_FILE_CORRUPT : MEC_OK;
+}
+extern "C" int mec_heal(mec_codec* c, const uint8_t* const* files, int64_t total, uint8_t* const* out_files) {
+  return mec_heal_prefer(c, files, nullptr, total, out_files, nullptr);
 }
 
 // Batched heal (BASELINE config 4): objects are independent, so a pool of codec handles — each with
 // its own streams and staging buffers — is driven by one host thread per handle; the H2D staging of one object then
 // overlaps the kernel and the D2H of the others (healObject's callers, cmd/global-heal.go:152, do the same with goroutines).
+// rcs[o] = MEC_ERR_FILE_CORRUPT means "healed, but a source reader of object o failed its digest" (see mec_heal_prefer);
+// the return value is the first result that is neither MEC_OK nor that.
 extern "C" int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobjects, const uint8_t* const* const* files,
                               const int64_t* totals, uint8_t* const* const* out_files, int* rcs) {
   if (!pool || npool <= 0 || nobjects < 0 || (nobjects > 0 && (!files || !totals || !out_files))) return MEC_ERR_INVALID_ARGUMENT;
@@ -657,7 +911,7 @@ extern "C" int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobject
       if (o >= nobjects) return;
       const int rc = mec_heal(pool[w], files[o], totals[o], out_files[o]);
       if (rcs) rcs[o] = rc;
-      if (rc != MEC_OK) {
+      if (rc != MEC_OK && rc != MEC_ERR_FILE_CORRUPT) {
         int expected = MEC_OK;
         first_err.compare_exchange_strong(expected, rc);
       }

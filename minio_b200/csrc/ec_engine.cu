@@ -49,6 +49,7 @@ struct StaticEntry {
   int k, m, sm16;
   KernelFn fast3d;    // TMA, S mod 16 == sm16, eb == kStaticEb, one 3-D request per tile
   KernelFn fast3d_auto;  // same, warp-autonomous pipeline (k + m == 16 and misaligned rows only), else nullptr
+  KernelFn fast3d_semi;  // same, barrier (B) warp-local
   KernelFn fast_auto, aligned_auto;  // warp-autonomous pipeline (k + m == 16 only), else nullptr
   KernelFn fast;      // TMA, S mod 16 == sm16, eb == kStaticEb
   KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb
@@ -57,25 +58,26 @@ struct StaticEntry {
 };
 static const StaticEntry kStaticTable[] = {
 #define X(K, M, A)                                                                                      \
-  {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, false, true>,                          \
-   (K + M == 16 && A != 0) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16 && A != 0), true> : nullptr, \
-   (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16)> : nullptr, \
-   (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16)> : nullptr,          \
-   fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, false>,                                        \
-   fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, false>,                                        \
-   fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0, false>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0, false>},
+  {K, M, A, fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, 0, true>,                          \
+   (K + M == 16 && A != 0) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16 && A != 0) ? 1 : 0, true> : nullptr, \
+   (K + M == 16 && A != 0) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16 && A != 0) ? 2 : 0, true> : nullptr, \
+   (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, (K + M == 16) ? 1 : 0> : nullptr, \
+   (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16) ? 1 : 0> : nullptr,          \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, 0>,                                        \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, 0>,                                        \
+   fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0, 0>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0, 0>},
     MEC_STATIC_CONFIGS(X)
 #undef X
 };
 // runtime-matrix kernels, indexed by row chunk {1, 2, 4}: a single rebuilt shard (the common single-drive
 // failure) costs a quarter of the masked XORs of a four-shard rebuild
-static const KernelFn kDynAligned[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, 0, 0, false>, fused_rs_hh_kernel<GfDynamic<2>, true, 0, 0, false>,
-                                        fused_rs_hh_kernel<GfDynamic<4>, true, 0, 0, false>};
-static const KernelFn kDynRuntime[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, kAlignRuntime, 0, false>,
-                                        fused_rs_hh_kernel<GfDynamic<2>, true, kAlignRuntime, 0, false>,
-                                        fused_rs_hh_kernel<GfDynamic<4>, true, kAlignRuntime, 0, false>};
-static const KernelFn kDynBytewise[3] = {fused_rs_hh_kernel<GfDynamic<1>, false, 0, 0, false>, fused_rs_hh_kernel<GfDynamic<2>, false, 0, 0, false>,
-                                         fused_rs_hh_kernel<GfDynamic<4>, false, 0, 0, false>};
+static const KernelFn kDynAligned[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, 0, 0, 0>, fused_rs_hh_kernel<GfDynamic<2>, true, 0, 0, 0>,
+                                        fused_rs_hh_kernel<GfDynamic<4>, true, 0, 0, 0>};
+static const KernelFn kDynRuntime[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, kAlignRuntime, 0, 0>,
+                                        fused_rs_hh_kernel<GfDynamic<2>, true, kAlignRuntime, 0, 0>,
+                                        fused_rs_hh_kernel<GfDynamic<4>, true, kAlignRuntime, 0, 0>};
+static const KernelFn kDynBytewise[3] = {fused_rs_hh_kernel<GfDynamic<1>, false, 0, 0, 0>, fused_rs_hh_kernel<GfDynamic<2>, false, 0, 0, 0>,
+                                         fused_rs_hh_kernel<GfDynamic<4>, false, 0, 0, 0>};
 
 // ------------------------------------------------------------------------------------------------
 // Run-time specialisation.  Decode matrices depend on which shards survived, so they cannot be
@@ -193,7 +195,7 @@ void* compile_specialised(const JitSpec& sp, bool load = true) {
   const char* bodies[] = {kJitHdr_rtc_compat_h, kJitHdr_gf256_h, kJitHdr_ec_device_cuh, kJitHdr_ec_kernel_cuh};
   nvrtcProgram prog = nullptr;
   const std::string expr_s = "mec::fused_rs_hh_kernel<mec::GfJit, true, " + std::to_string(sp.align) + ", " + std::to_string(sp.eb_t) +
-                             ", false, " + (sp.rows3d ? "true" : "false") + ">";
+                             ", 0, " + (sp.rows3d ? "true" : "false") + ">";
   const char* expr = expr_s.c_str();
   if (api.create(&prog, src.c_str(), "mec_jit.cu", 4, bodies, names) != NVRTC_SUCCESS) return nullptr;
   api.add_name(prog, expr);
@@ -338,7 +340,9 @@ void* Engine::jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t,
 }
 
 Engine::Engine(int device) : device_(device) {}
-Engine::~Engine() {}
+Engine::~Engine() {
+  if (claim_slots_) { cudaSetDevice(device_); cudaFree(claim_slots_); }
+}
 
 int Engine::init() {
   int count = 0;
@@ -462,7 +466,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       any_misaligned |= (off & 15) != 0;
     }
     // every row 16-byte aligned and a kernel instantiated for ALIGN == 0: TMA writes the hash threads' rows directly
-    direct = use_tma && !any_misaligned && !(opt.use_auto && se && se->aligned_auto) && (!se || eb == kStaticEb);
+    direct = use_tma && !any_misaligned && !(opt.use_auto == 1 && se && se->aligned_auto) && (!se || eb == kStaticEb);
     if (use_tma) {
       p.tma_mode = kLoadTmaBlocks2D;
       const uint64_t stride = d.nblocks > 1 ? static_cast<uint64_t>(d.in_block_stride) : static_cast<uint64_t>(d.in_block_len);
@@ -470,7 +474,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       const int sm16 = static_cast<int>(d.S & 15);
       const int64_t row_stride = static_cast<int64_t>(d.S) & ~15ll;
       if (se && !opt.no_rows3d && eb == kStaticEb && sm16 == se->sm16 && d.in_block_len == d.in_block_stride &&
-          !(opt.use_auto && se->aligned_auto && sm16 == 0)) {
+          !(opt.use_auto == 1 && se->aligned_auto && sm16 == 0)) {
         const int rg = direct ? d.k : rows_per_request_3d(d.k, sm16, eb);  // shard rows per request (ec_kernel.cuh)
         const int raw3 = direct ? kRowPitch : raw_row_3d(d.k, sm16, eb, rg);
         const int shift_max = group_shift_3d((d.k - 1) / rg, sm16, rg);
@@ -530,9 +534,10 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   if (se) {
     const int sm16 = static_cast<int>(d.S & 15);
     if (!use_tma) fn = se->bytewise;
-    else if (rows3d) fn = (opt.use_auto && se->fast3d_auto && !direct) ? se->fast3d_auto : se->fast3d;
-    else if (eb == kStaticEb && sm16 == se->sm16) fn = (opt.use_auto && se->fast_auto) ? se->fast_auto : se->fast;
-    else if (eb == kStaticEb && sm16 == 0) fn = (opt.use_auto && se->aligned_auto) ? se->aligned_auto : se->aligned;
+    else if (rows3d) fn = (opt.use_auto == 1 && se->fast3d_auto && !direct) ? se->fast3d_auto
+                          : ((opt.use_auto == 2 && se->fast3d_semi && !direct) ? se->fast3d_semi : se->fast3d);
+    else if (eb == kStaticEb && sm16 == se->sm16) fn = (opt.use_auto == 1 && se->fast_auto) ? se->fast_auto : se->fast;
+    else if (eb == kStaticEb && sm16 == 0) fn = (opt.use_auto == 1 && se->aligned_auto) ? se->aligned_auto : se->aligned;
     else fn = se->runtime;
   } else {
     const int rc = d.r <= 1 ? 0 : (d.r == 2 ? 1 : 2);
@@ -567,6 +572,13 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     grid = (ngroups + passes - 1) / passes;
   }
 
+  // dynamic deal of groups: worth a counter only when CTAs make more than one pass
+  constexpr uint32_t kClaimSlots = 1024;
+  if (!opt.static_groups && ngroups > grid) {
+    if (!claim_slots_) MEC_CUDA_OK(cudaMalloc(&claim_slots_, kClaimSlots * sizeof(uint32_t)));
+    p.work_counter = claim_slots_ + (claim_next_++ % kClaimSlots);
+    MEC_CUDA_OK(cudaMemsetAsync(p.work_counter, 0, sizeof(uint32_t), st));
+  }
   void* args[] = {&p, &maps};
   MEC_CUDA_OK(cudaLaunchKernel(kfn, dim3(static_cast<unsigned>(grid)), dim3(static_cast<unsigned>(threads)), args, smem, st));
   MEC_CUDA_OK(cudaGetLastError());

@@ -57,6 +57,8 @@ struct EngineOptions {
   int no_rows3d = 0;       // 1: never use the one-request-per-tile 3-D TMA fetch
   int use_auto = 0;        // 1: warp-autonomous pipeline (no CTA barriers) when k + r == 16; measured slower, off by default
   int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
+  int static_groups = 1;   // 1 (default): erasure-block groups are dealt to CTAs statically (g += gridDim.x); 0: through a claim counter —
+                           // measured equal on a dedicated GPU (profiles/r2_kernel_ab.md), useful when SMs are shared or uneven
 };
 
 class Engine {
@@ -79,6 +81,8 @@ class Engine {
   void* encode_tiled_ = nullptr;  // cuTensorMapEncodeTiled
   int64_t launches_ = 0;
   int64_t jit_launches_ = 0;
+  uint32_t* claim_slots_ = nullptr;  // ring of per-launch group-claim counters (device)
+  uint32_t claim_next_ = 0;
   // run-time specialised kernels, keyed by (k, r, matrix bytes)
   void* jit_kernel(int k, int r, const uint8_t* coef, int align, int eb_t, bool rows3d, bool hash_out, int mode, int64_t in_bytes);
 };

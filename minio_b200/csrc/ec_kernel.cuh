@@ -65,6 +65,7 @@ struct FusedParams {
   uint8_t* corrupt;                // optional [nblocks][k], set to 1 on digest mismatch
   uint64_t key[4];                 // HighwayHash key (cmd/bitrot.go:37 for bitrot)
   uint8_t coef[kMaxR][kMaxK];      // runtime matrix (GfDynamic only)
+  uint32_t* work_counter;          // optional: groups beyond the first of every CTA are claimed from this counter (zeroed per launch)
 };
 
 // ------------------------------------------------------------------ GF policies
@@ -189,8 +190,8 @@ __host__ __device__ constexpr int fused_min_blocks() {
   const int b = by_regs < by_smem ? by_regs : by_smem;
   return b > 0 ? b : 1;
 }
-template <class GF, bool USE_TMA, int ALIGN, int EB_T, bool AUTO, bool ROWS3D = false>
-__global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_blocks<GF, ALIGN, EB_T, ROWS3D, fused_is_direct(USE_TMA, ALIGN, AUTO)>())) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
+template <class GF, bool USE_TMA, int ALIGN, int EB_T, int AUTO_MODE, bool ROWS3D = false>
+__global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_blocks<GF, ALIGN, EB_T, ROWS3D, fused_is_direct(USE_TMA, ALIGN, AUTO_MODE == 1)>())) fused_rs_hh_kernel(const __grid_constant__ FusedParams p,
                                                                          const __grid_constant__ TmaMaps maps) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int k = GF::kIsStatic ? GF::K : p.k;
@@ -200,7 +201,11 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   const int tid = threadIdx.x, nthr = blockDim.x;
   const int warp_id = __shfl_sync(0xffffffffu, tid >> 5, 0);  // provably warp-uniform
   const bool warp0 = warp_id == 0;
+  // AUTO_MODE 1: warp-autonomous pipeline (no CTA barrier); 2: barrier (A) kept, barrier (B) warp-local (k + r == 16, !DIRECT)
+  constexpr bool AUTO = AUTO_MODE == 1;
   constexpr bool DIRECT = fused_is_direct(USE_TMA, ALIGN, AUTO);
+  constexpr bool WARP_B = AUTO_MODE == 2 && !DIRECT && USE_TMA;
+  static_assert(AUTO_MODE == 0 || GF::kIsStatic, "warp-local hand-offs need one warp per erasure block: compile-time (k, r) with k + r == 16");
   constexpr int kK3 = GF::K > 0 ? GF::K : 1, kSm3 = ALIGN > 0 ? ALIGN : 0, kEb3 = EB_T > 0 ? EB_T : 1;
   constexpr int kRG = ROWS3D ? (DIRECT ? kK3 : rows_per_request_3d(kK3, kSm3, kEb3)) : 1;  // shard rows per 3-D request
   constexpr int kRaw3 = ROWS3D ? (DIRECT ? kRowPitch : raw_row_3d(kK3, kSm3, kEb3)) : kRawRow;
@@ -264,7 +269,14 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
   const int64_t ngroups = (p.nblocks + eb - 1) / eb;
   uint32_t it = 0;  // running tile counter (mbarrier phase bookkeeping)
 
-  for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+  // Groups are dealt dynamically when the launch brings a counter: CTA c starts with group c, every further group is claimed
+  // with one atomicAdd issued at the START of the group before it (its latency hides behind a whole group of work).  With the
+  // static deal (g += gridDim.x) the CTAs that own one more group than the others decide the run time — 2.47 groups per CTA for
+  // the 10240-block stream leaves a third pass in which some SMs have 4 CTAs and others 3.
+  uint32_t* s_next = reinterpret_cast<uint32_t*>(bars + 3);
+  for (int64_t g = blockIdx.x; g < ngroups;) {
+    uint32_t claimed = 0;
+    if (p.work_counter != nullptr && tid == 0) claimed = atomicAdd(p.work_counter, 1u);
     const int64_t b0 = g * eb;
     const int nb = (p.nblocks - b0) < eb ? static_cast<int>(p.nblocks - b0) : eb;
     const bool hh_live = hh_thread && e_hh < nb;
@@ -518,8 +530,10 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
       }
 
       hh_step(i, fast_);
-      if constexpr (AUTO && USE_TMA) __syncwarp();  // (B) this warp's rows may be overwritten
-      else __syncthreads();                          // (B) aligned + output tiles may be overwritten
+      // (B) aligned + output rows may be overwritten.  With one warp per erasure block the rows a warp writes in GF(i+1) are
+      // read by its own hash lanes only, so the hand-off is warp-local; the raw tile is protected by barrier (A) / the mbarrier
+      if constexpr ((AUTO && USE_TMA) || WARP_B) __syncwarp();
+      else __syncthreads();
     };
     static_assert(kTile == 256, "tile shift");
     const int nfast = (nb == eb) ? (S >> 8) : 0;
@@ -549,6 +563,14 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
       }
     }
     it += static_cast<uint32_t>(ntiles);
+    if (p.work_counter != nullptr) {
+      if (tid == 0) *s_next = claimed;
+      __syncthreads();
+      g = static_cast<int64_t>(gridDim.x) + *s_next;
+      __syncthreads();  // nobody may still be reading the slot when the next group's claim lands
+    } else {
+      g += gridDim.x;
+    }
   }
 }
 

@@ -1,0 +1,212 @@
+"""GPU tests of the round-2 host paths: pipelined Decode / Heal with DMA sinks, scatter-gather Encode, Heal's bitrot side-band,
+NUMA-local pinned buffers, the parity-only tail block, dynamic group claiming — each bit-exact against the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+MiB = 1 << 20
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import minio_b200
+    assert minio_b200.device_count() > 0, "no CUDA device"
+    return minio_b200
+
+
+def rand(n, seed):
+    return np.random.default_rng(seed).integers(0, 256, n, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("k,m,bs,length", [(12, 4, MiB, 5 * MiB + 4321), (12, 4, MiB, 70 * MiB + 17), (4, 2, MiB, 4 * MiB),
+                                           (6, 2, 512 * 1024, MiB + 3), (16, 4, MiB, 3 * MiB), (8, 8, 256 * 1024, 9 * MiB + 1),
+                                           (2, 2, MiB, 5), (12, 4, MiB, MiB - 1)])
+def test_encode_sg_vs_oracle(mb, oracle, k, m, bs, length):
+    """mec_encode_sg: parity frames by DMA, data digests separately; data frames = digest + the caller's own slice."""
+    data = rand(length, length % 1009)
+    want, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    c = mb.Codec(k, m, bs)
+    files, dd = c.encode_sg(data)
+    S = c.shard_size()
+    for j in range(m):
+        assert np.array_equal(files[k + j], want[k + j]), j
+    # rebuild the data drives' part files the way a writer would: digest, then the slice of the source (zero padded)
+    nb = -(-length // bs)
+    for i in range(k):
+        out, pos = np.zeros(want[i].size, dtype=np.uint8), 0
+        for b in range(nb):
+            blen = min(bs, length - b * bs)
+            per = -(-blen // k)
+            out[pos:pos + 32] = dd[b, i]
+            lo = min(i * per, blen); hi = min((i + 1) * per, blen)
+            out[pos + 32:pos + 32 + (hi - lo)] = data[b * bs + lo:b * bs + hi]
+            pos += 32 + per
+        assert pos == want[i].size and np.array_equal(out, want[i]), i
+    c.close()
+
+
+def test_encode_frames_into_pinned_numa_buffers(mb, oracle):
+    """mec_encode writing every frame by DMA into mec_alloc_pinned_on buffers; decode straight back out of them."""
+    k, m, bs, length = 12, 4, MiB, 37 * MiB + 12345
+    L = mb.lib()
+    node = L.mec_device_numa_node(0)
+    assert node >= -1
+    data = mb.capi.pinned_array(length, device=0)
+    data[:] = rand(length, 5)
+    assert L.mec_is_pinned(data.ctypes.data) == 1
+    want, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, data)
+    c = mb.Codec(k, m, bs)
+    fsz = c.bitrot_file_size(length)
+    files = [mb.capi.pinned_array(fsz, device=0) for _ in range(k + m)]
+    for f in files:
+        f[:] = 0xA5
+    ptrs = (C.c_void_p * (k + m))(*[f.ctypes.data for f in files])
+    rc = L.mec_encode(c.h, data.ctypes.data, length, ptrs, k + 1)
+    assert rc == length
+    for i in range(k + m):
+        assert np.array_equal(files[i], want[i]), i
+    dst = mb.capi.pinned_array(length, device=0)
+    fptrs = (C.c_void_p * (k + m))(*[None if i in (1, 4, 9, 13) else files[i].ctypes.data for i in range(k + m)])
+    hint = C.c_int(0)
+    rc = L.mec_decode(c.h, fptrs, 0, length, length, dst.ctypes.data, C.byref(hint))
+    assert rc == length and hint.value == 0 and np.array_equal(dst, data)
+    c.close()
+    for a in files + [data, dst]:
+        L.mec_free_pinned(a.ctypes.data)
+
+
+def test_bind_thread_to_device_is_harmless(mb):
+    L = mb.lib()
+    import os
+    before = os.sched_getaffinity(0)
+    node = L.mec_bind_thread_to_device(0)
+    after = os.sched_getaffinity(0)
+    assert after <= before and len(after) > 0
+    assert node == -1 or node == L.mec_device_numa_node(0)
+    os.sched_setaffinity(0, before)
+
+
+@pytest.mark.parametrize("offset,length", [(0, 70 * MiB + 17), (MiB - 1, 2), (3 * MiB + 5, 40 * MiB), (69 * MiB, MiB + 17),
+                                           (70 * MiB, 17), (12345, 66 * MiB), (35 * MiB, 0), (0, 1)])
+def test_pipelined_decode_ranges(mb, oracle, offset, length):
+    """Multi-chunk Decode (3 slots x 32-block chunks) over every kind of range edge, with four shards offline."""
+    k, m, bs, size = 12, 4, MiB, 70 * MiB + 17
+    data = rand(size, 77)
+    c = mb.Codec(k, m, bs)
+    files = c.encode(data)
+    srcs = [None if i in (0, 3, 11, 14) else files[i] for i in range(k + m)]
+    out, hint = c.decode(srcs, offset, length, size)
+    assert hint == 0 and np.array_equal(out, data[offset:offset + length])
+    c.close()
+
+
+def test_pipelined_decode_failover_mid_stream(mb, oracle):
+    """Bitrot in the middle of a long part: chunks submitted behind the bad block are discarded, the range resumes at
+    the bad block with the next reader, and the bytes match the oracle's block-sequential parallelReader."""
+    k, m, bs, size = 12, 4, MiB, 100 * MiB + 1000
+    data = rand(size, 78)
+    c = mb.Codec(k, m, bs)
+    files = c.encode(data)
+    S = c.shard_size()
+    bad = [f.copy() for f in files]
+    bad[2][50 * (32 + S) + 32 + 999] ^= 0x10     # data shard 2, block 50
+    bad[7][51 * (32 + S) + 3] ^= 0x01            # digest of shard 7, block 51
+    bad[12][97 * (32 + S) + 40] ^= 0xFF          # parity shard 12 (first stand-in), block 97
+    out, hint = c.decode(bad, 0, size, size)
+    assert hint == -7 and np.array_equal(out, data)
+    rc, ref, corrupt = oracle.erasure_decode(k, m, bs, oracle.HIGHWAYHASH256S, bad, [1] * 16, 0, size, size)
+    assert rc == size and np.array_equal(ref, data)
+    assert c.stat("corrupt_shards") == int(sum(corrupt))
+    c.close()
+
+
+def test_heal_reports_bitrot_in_a_source(mb, oracle):
+    """Erasure.Heal returns errFileCorrupt AFTER writing the healed shards when a source reader failed its digest
+    (cmd/erasure-decode.go:338-341,366); the drop-in must not swallow it."""
+    k, m, bs, size = 12, 4, MiB, 40 * MiB + 333
+    data = rand(size, 79)
+    c = mb.Codec(k, m, bs)
+    files = c.encode(data)
+    S = c.shard_size()
+    stale = [i in (0, 15) for i in range(16)]
+    srcs = [None if stale[i] else files[i].copy() for i in range(16)]
+    srcs[4][20 * (32 + S) + 32 + 5] ^= 0x02
+    outs, rc, corrupt = c.heal(srcs, stale, size, report=True)
+    assert rc == -7 and list(np.nonzero(corrupt)[0]) == [4]
+    for i in (0, 15):
+        assert np.array_equal(outs[i], files[i])
+    with pytest.raises(mb.MecError) as ei:
+        c.heal(srcs, stale, size)
+    assert ei.value.code == -7
+    # clean sources: MEC_OK, and the prefer hint does not change the bytes
+    srcs[4] = files[4]
+    outs, rc, corrupt = c.heal(srcs, stale, size, prefer=[i % 2 for i in range(16)], report=True)
+    assert rc == 0 and not corrupt.any()
+    for i in (0, 15):
+        assert np.array_equal(outs[i], files[i])
+    c.close()
+
+
+def test_parity_only_tail_block(mb, oracle):
+    """mec_encode_blocks_device with d_digests == NULL and a length that is not a block multiple: the tail launch must not
+    hash either."""
+    import torch
+    k, m, bs = 12, 4, MiB
+    length = 2 * bs + 4321
+    data = rand(length, 80)
+    dev = torch.device("cuda:0")
+    src = torch.zeros(length + 4096, dtype=torch.uint8, device=dev)
+    src[:length] = torch.from_numpy(data).to(dev)
+    c = mb.Codec(k, m, bs)
+    S = c.shard_size()
+    pitch = (S + 15) // 16 * 16
+    par = torch.zeros((3 * m, pitch), dtype=torch.uint8, device=dev)
+    guard = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
+    c.encode_blocks_device(src.data_ptr(), length, par.data_ptr(), pitch, 0, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert int(guard.sum().item()) == 0
+    hp = par.cpu().numpy()
+    for b in range(3):
+        blk = data[b * bs:(b + 1) * bs]
+        sh = oracle.encode_data(k, m, blk, fast=True)
+        per = sh[0].size
+        for j in range(m):
+            assert np.array_equal(hp[b * m + j, :per], sh[k + j]), (b, j)
+    # d_corrupt without d_digests is refused instead of silently skipping the bitrot check
+    fp = (32 + S + 15) // 16 * 16
+    rc = mb.lib().mec_reconstruct_device(c.h, (C.c_void_p * 16)(*[par.data_ptr()] * 16), fp, 1,
+                                         np.ones(16, dtype=np.uint8).ctypes.data, 0, par.data_ptr(), pitch, None, par.data_ptr(), None)
+    assert rc == -12
+    c.close()
+
+
+@pytest.mark.parametrize("static_groups", [0, 1])
+def test_group_claiming_modes_agree(mb, oracle, static_groups):
+    """Dynamic group claiming (several passes per CTA) and the static deal produce the same bytes."""
+    import torch
+    k, m, bs, nblocks = 12, 4, MiB, 9000   # > 7 CTAs x 148 SMs x 4 blocks: every CTA claims at least one more group
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev); g.manual_seed(1234)
+    src = torch.randint(0, 256, (nblocks * bs,), dtype=torch.uint8, device=dev, generator=g)
+    S = 87382
+    pitch = (S + 15) // 16 * 16
+    par = torch.zeros((nblocks * m, pitch), dtype=torch.uint8, device=dev)
+    dig = torch.zeros((nblocks, k + m, 32), dtype=torch.uint8, device=dev)
+    c = mb.Codec(k, m, bs)
+    c.set_option("static_groups", static_groups)
+    c.encode_blocks_device(src.data_ptr(), src.numel(), par.data_ptr(), pitch, dig.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    for b in (0, 4143, 4144, 4147, 8287, 8288, 8999):
+        blk = src[b * bs:(b + 1) * bs].cpu().numpy()
+        sh = oracle.encode_data(k, m, blk, fast=True)
+        hp = par[b * m:(b + 1) * m, :S].cpu().numpy()
+        hd = dig[b].cpu().numpy()
+        for j in range(m):
+            assert np.array_equal(hp[j], sh[k + j]), (b, j)
+        for i in range(k + m):
+            assert hd[i].tobytes() == oracle.hh256(sh[i], fast=True), (b, i)
+    # every block was written exactly once: no digest row is left zero
+    assert bool((dig.view(torch.int64).reshape(nblocks, -1) != 0).any(dim=1).all().item())
+    c.close()
