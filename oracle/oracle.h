@@ -137,6 +137,17 @@ void orc_hh256_fast(const uint8_t key[32], const uint8_t *p, size_t n, uint8_t o
 double orc_encode_hash_blocks_mt(int k, int m, int64_t block_size, const uint8_t *src,
                                  int64_t nblocks, uint8_t *parity, uint8_t *digests, int threads,
                                  int reps);
+/* Persistent worker pool for the CPU arm (threads created once, pinned over all allowed CPUs, source first-touched by the
+ * worker that encodes it): orc_pool_fill writes synthetic bytes into src (nblocks * block_size) and clears the outputs;
+ * orc_pool_encode_hash runs `reps` passes of SIMD RS encode + HighwayHash of every shard and returns the seconds between
+ * releasing the workers and the last one finishing. */
+typedef struct orc_pool orc_pool;
+orc_pool *orc_pool_new(int threads);
+void orc_pool_fill(orc_pool *p, int k, int m, int64_t block_size, uint8_t *src, int64_t nblocks, uint8_t *parity, uint8_t *digests, uint64_t seed);
+double orc_pool_encode_hash(orc_pool *p, int k, int m, int64_t block_size, const uint8_t *src, int64_t nblocks, uint8_t *parity,
+                            uint8_t *digests, int reps);
+void orc_pool_free(orc_pool *p);
+
 #ifdef __cplusplus
 }
 #endif

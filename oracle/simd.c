@@ -212,3 +212,130 @@ double orc_encode_hash_blocks_mt(int k, int m, int64_t bs, const uint8_t *src, i
   free(th); free(args); free(mat);
   return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ---------------- persistent worker pool (the CPU arm of bench.py) ----------------
+ * klauspost/reedsolomon keeps its goroutines for the life of the encoder (WithAutoGoroutines, cmd/erasure-coding.go:63) and
+ * MinIO's request goroutines run on every core of both sockets.  The stand-in: T pthreads created ONCE (outside every timed
+ * region), pinned round-robin over the CPUs the process may use, each first-touching the source blocks it will later
+ * encode (so its pages are node-local), then released per run by a generation counter.  A run is timed from the moment
+ * the workers are released to the moment the last one reports back. */
+#ifndef _GNU_SOURCE
+#define _GNU_SOURCE
+#endif
+#include <sched.h>
+
+struct orc_pool {
+  int threads, stop;
+  pthread_t *th;
+  pthread_mutex_t mu;
+  pthread_cond_t cv_go, cv_done;
+  uint64_t gen;
+  int pending;
+  /* job */
+  int job, k, m, reps;
+  int64_t bs, nblocks;
+  uint8_t *src, *parity, *digests;
+  const uint8_t *rows;
+  uint64_t seed;
+  struct orc_pool_worker *w;
+};
+struct orc_pool_worker { struct orc_pool *p; int tid; };
+
+static void pool_fill(struct orc_pool *p, int tid) {  /* job 1: first touch + synthetic bytes, same block deal as job 2 */
+  for (int64_t b = tid; b < p->nblocks; b += p->threads) {
+    uint64_t x = p->seed ^ (0x9E3779B97F4A7C15ull * (uint64_t)(b + 1));
+    uint64_t *q = (uint64_t *)(p->src + b * p->bs);
+    for (int64_t i = 0; i < p->bs / 8; i++) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; q[i] = x; }
+    if (p->parity) memset(p->parity + (size_t)b * p->m * orc_shard_size(p->bs, p->k), 0, (size_t)p->m * orc_shard_size(p->bs, p->k));
+    if (p->digests) memset(p->digests + (size_t)b * (p->k + p->m) * 32, 0, (size_t)(p->k + p->m) * 32);
+  }
+}
+
+static void *pool_main(void *vp) {
+  struct orc_pool_worker *w = (struct orc_pool_worker *)vp;
+  struct orc_pool *p = w->p;
+  uint64_t seen = 0;
+  for (;;) {
+    pthread_mutex_lock(&p->mu);
+    while (!p->stop && p->gen == seen) pthread_cond_wait(&p->cv_go, &p->mu);
+    if (p->stop) { pthread_mutex_unlock(&p->mu); return NULL; }
+    seen = p->gen;
+    pthread_mutex_unlock(&p->mu);
+    if (p->job == 1) {
+      pool_fill(p, w->tid);
+    } else {
+      mt_arg a = {p->k, p->m, w->tid, p->threads, p->reps, p->bs, p->nblocks, p->src, p->parity, p->digests, p->rows};
+      mt_worker(&a);
+    }
+    pthread_mutex_lock(&p->mu);
+    if (--p->pending == 0) pthread_cond_signal(&p->cv_done);
+    pthread_mutex_unlock(&p->mu);
+  }
+}
+
+orc_pool *orc_pool_new(int threads) {
+  if (threads < 1) threads = 1;
+  orc_pool *p = (orc_pool *)calloc(1, sizeof(*p));
+  p->threads = threads;
+  p->th = (pthread_t *)malloc(sizeof(pthread_t) * threads);
+  p->w = (struct orc_pool_worker *)malloc(sizeof(struct orc_pool_worker) * threads);
+  pthread_mutex_init(&p->mu, NULL);
+  pthread_cond_init(&p->cv_go, NULL);
+  pthread_cond_init(&p->cv_done, NULL);
+  orc_gf_mul(1, 1); /* tables exist before any worker runs */
+  cpu_set_t allowed;
+  int cpus[CPU_SETSIZE], ncpu = 0;
+  if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+    for (int c = 0; c < CPU_SETSIZE; c++)
+      if (CPU_ISSET(c, &allowed)) cpus[ncpu++] = c;
+  for (int t = 0; t < threads; t++) {
+    p->w[t].p = p; p->w[t].tid = t;
+    pthread_create(&p->th[t], NULL, pool_main, &p->w[t]);
+    if (ncpu > 0) {  /* spread over everything the process may use — both sockets on a two-socket host */
+      cpu_set_t one;
+      CPU_ZERO(&one);
+      CPU_SET(cpus[(int)(((int64_t)t * ncpu) / threads)], &one);
+      pthread_setaffinity_np(p->th[t], sizeof(one), &one);
+    }
+  }
+  return p;
+}
+
+static double pool_run(orc_pool *p) {
+  struct timespec t0, t1;
+  pthread_mutex_lock(&p->mu);
+  p->pending = p->threads;
+  p->gen++;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_cond_broadcast(&p->cv_go);
+  while (p->pending > 0) pthread_cond_wait(&p->cv_done, &p->mu);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  pthread_mutex_unlock(&p->mu);
+  return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+}
+
+void orc_pool_fill(orc_pool *p, int k, int m, int64_t bs, uint8_t *src, int64_t nblocks, uint8_t *parity, uint8_t *digests, uint64_t seed) {
+  p->job = 1; p->k = k; p->m = m; p->bs = bs; p->src = src; p->nblocks = nblocks; p->parity = parity; p->digests = digests; p->seed = seed;
+  pool_run(p);
+}
+
+double orc_pool_encode_hash(orc_pool *p, int k, int m, int64_t bs, const uint8_t *src, int64_t nblocks, uint8_t *parity,
+                            uint8_t *digests, int reps) {
+  uint8_t *mat = (uint8_t *)malloc((size_t)(k + m) * k);
+  orc_rs_matrix(k, m, mat);
+  p->job = 2; p->k = k; p->m = m; p->bs = bs; p->src = (uint8_t *)src; p->nblocks = nblocks; p->parity = parity; p->digests = digests;
+  p->reps = reps; p->rows = mat + (size_t)k * k;
+  double s = pool_run(p);
+  free(mat);
+  return s;
+}
+
+void orc_pool_free(orc_pool *p) {
+  if (!p) return;
+  pthread_mutex_lock(&p->mu);
+  p->stop = 1;
+  pthread_cond_broadcast(&p->cv_go);
+  pthread_mutex_unlock(&p->mu);
+  for (int t = 0; t < p->threads; t++) pthread_join(p->th[t], NULL);
+  free(p->th); free(p->w); free(p);
+}

@@ -67,6 +67,14 @@ def lib():
     L.orc_rs_encode_fast.restype = None
     L.orc_encode_hash_blocks_mt.restype = C.c_double
     L.orc_encode_hash_blocks_mt.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    L.orc_pool_new.restype = C.c_void_p
+    L.orc_pool_new.argtypes = [C.c_int]
+    L.orc_pool_free.argtypes = [C.c_void_p]
+    L.orc_pool_free.restype = None
+    L.orc_pool_fill.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_uint64]
+    L.orc_pool_fill.restype = None
+    L.orc_pool_encode_hash.restype = C.c_double
+    L.orc_pool_encode_hash.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]
     _LIB = L
     return L
 
