@@ -188,6 +188,18 @@ int mec_bitrot_verify_whole(mec_codec* c, int algo, const uint8_t* file, int64_t
  * bytes after the last message), digest i at d_digests + i*64.  Asynchronous on `cuda_stream`. */
 int mec_whole_hash_device(mec_codec* c, int algo, const uint8_t* d_msgs, int64_t pitch, int64_t msg_len, int64_t count,
                           uint8_t* d_digests, void* cuda_stream);
+/* Erasure.Decode / Erasure.Heal over whole-file bitrot readers (wholeBitrotReader.ReadAt, cmd/bitrot-whole.go:66-81): files[i] is
+ * the RAW shard file of drive i (mec_shard_file_size(total) bytes, NULL = offline), sums + i*64 its expected digest (the
+ * checksum xl.meta keeps for whole-file algorithms).  A reader whose whole-file digest does not match is errFileCorrupt: it is
+ * dropped and the next drive in index order takes its place (cmd/xl-storage.go:1931-1950, cmd/erasure-decode.go:196-199).
+ * mec_decode_whole returns bytes written (*heal_hint = MEC_ERR_FILE_CORRUPT when a reader was dropped but the read succeeded).
+ * mec_heal_whole rebuilds every shard file with out_files[i] != NULL, writes its digest to out_sums + i*64 (optional) and returns
+ * MEC_OK, or MEC_ERR_FILE_CORRUPT when it healed but met bitrot in a source (corrupt[i], optional, names the readers).
+ * The codec's algorithm must be SHA256, BLAKE2b512 or HighwayHash256. */
+int64_t mec_decode_whole(mec_codec* c, const uint8_t* const* files, const uint8_t* sums, int64_t offset, int64_t length,
+                         int64_t total_length, uint8_t* dst, int* heal_hint);
+int mec_heal_whole(mec_codec* c, const uint8_t* const* files, const uint8_t* sums, int64_t total_length,
+                   uint8_t* const* out_files, uint8_t* out_sums, uint8_t* corrupt);
 int mec_digest_size(int algo);
 
 /* bitrotVerify (cmd/bitrot.go:164) for the streaming algorithm: scans a whole shard file. */

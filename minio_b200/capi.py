@@ -59,6 +59,9 @@ def lib():
     L.mec_encode_sg.restype = i64
     L.mec_encode_sg.argtypes = [vp, vp, i64, vp, vp, i32]
     L.mec_heal_prefer.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.mec_decode_whole.restype = i64
+    L.mec_decode_whole.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
+    L.mec_heal_whole.argtypes = [vp, vp, vp, i64, vp, vp, vp]
     L.mec_encode_blocks.argtypes = [vp, vp, i64, vp, vp]
     L.mec_encode_blocks_device.argtypes = [vp, vp, i64, vp, i64, vp, vp]
     L.mec_reconstruct_frames.argtypes = [vp, vp, i64, i64, vp, i32, vp, vp]
@@ -271,6 +274,37 @@ class Codec:
             raise MecError(rc, "mec_encode_whole")
         ds = lib().mec_digest_size(self.algo)
         return files, [sums[i, :ds].tobytes() for i in range(self.n)]
+
+    def decode_whole(self, files, sums, offset, length, total):
+        """Erasure.Decode over wholeBitrotReaders: files = raw shard files (None = offline), sums = their expected digests."""
+        files = [None if f is None else _u8(f) for f in files]
+        sm = np.zeros((self.n, 64), dtype=np.uint8)
+        for i, d in enumerate(sums):
+            if d is not None:
+                sm[i, :len(d)] = np.frombuffer(bytes(d), dtype=np.uint8)
+        dst = np.zeros(max(length, 1), dtype=np.uint8)
+        hint = C.c_int(0)
+        rc = lib().mec_decode_whole(self.h, _ptrs(files), sm.ctypes.data, offset, length, total, dst.ctypes.data, C.byref(hint))
+        if rc < 0:
+            raise MecError(rc, "mec_decode_whole")
+        return dst[:length], hint.value
+
+    def heal_whole(self, files, sums, stale, total):
+        """-> (out_files, out_sums, rc, corrupt): rc is 0 or -7 (healed, bitrot met in a source)."""
+        files = [None if f is None else _u8(f) for f in files]
+        sm = np.zeros((self.n, 64), dtype=np.uint8)
+        for i, d in enumerate(sums):
+            if d is not None:
+                sm[i, :len(d)] = np.frombuffer(bytes(d), dtype=np.uint8)
+        flen = self.shard_file_size(total)
+        outs = [np.zeros(flen, dtype=np.uint8) if stale[i] else None for i in range(self.n)]
+        osum = np.zeros((self.n, 64), dtype=np.uint8)
+        corrupt = np.zeros(self.n, dtype=np.uint8)
+        rc = lib().mec_heal_whole(self.h, _ptrs(files), sm.ctypes.data, total, _ptrs(outs), osum.ctypes.data, corrupt.ctypes.data)
+        if rc and rc != -7:
+            raise MecError(rc, "mec_heal_whole")
+        ds = lib().mec_digest_size(self.algo)
+        return outs, [osum[i, :ds].tobytes() if stale[i] else None for i in range(self.n)], rc, corrupt
 
     def whole_hash(self, algo, msgs, msg_len, count):
         msgs = _u8(msgs)

@@ -1096,6 +1096,256 @@ extern "C" int64_t mec_encode_whole(mec_codec* c, const uint8_t* src, int64_t le
 }
 
 // ------------------------------------------------------------------------------------------------
+// Decode / Heal over whole-file bitrot readers (cmd/bitrot-whole.go:66-81): a wholeBitrotReader reads its shard file on the first
+// ReadAt and checks the digest of the WHOLE file (xlStorage.ReadFile with a verifier, cmd/xl-storage.go:1931-1950) — a mismatch
+// is errFileCorrupt, the reader is dropped and parallelReader moves on to the next drive.  Here: the first k readers in index
+// order are staged and hashed on the GPU (whole_hash_kernel), failing ones are replaced by the next alive reader until k
+// verified shard files sit on the device; the rebuild then runs on those raw shards (no per-block digests exist in this format).
+static int require_whole(mec_codec* c) {
+  if (c->algo == MEC_HIGHWAYHASH256S) {
+    set_last_error("whole-file entry points need a codec created with SHA256, BLAKE2b512 or HighwayHash256");
+    return MEC_ERR_INVALID_ARGUMENT;
+  }
+  return ensure_engine(c);
+}
+
+// stage + verify: on return chosen[0..k) (ascending) name k verified files, file chosen[t] at s.aux + t*fpitch
+static int stage_verified_whole(mec_codec* c, const uint8_t* const* files, const uint8_t* sums, int64_t sfs, uint8_t* alive,
+                                uint8_t* corrupt, int* chosen, int64_t fpitch, Slot& s) {
+  const int k = c->k, n = c->n, ds = mec_digest_size(c->algo);
+  int rc;
+  if ((rc = s.aux.ensure(static_cast<size_t>(k * fpitch + 256)))) return rc;
+  if ((rc = s.dig.ensure(static_cast<size_t>(k * 64)))) return rc;
+  if ((rc = s.hdig.ensure(static_cast<size_t>(k * 64)))) return rc;
+  int slot_of[kMaxShards];  // which arena position holds file i (-1 = not staged)
+  for (int i = 0; i < n; i++) slot_of[i] = -1;
+  bool verified[kMaxShards] = {};
+  for (;;) {
+    int want[kMaxShards], nw = 0;
+    for (int i = 0; i < n && nw < k; i++)
+      if (alive[i]) want[nw++] = i;
+    if (nw < k) return MEC_ERR_READ_QUORUM;
+    // arena positions: keep verified files where they are, give the newcomers the free positions
+    bool used[kMaxK] = {};
+    for (int q = 0; q < k; q++)
+      if (slot_of[want[q]] >= 0) used[slot_of[want[q]]] = true;
+    int fresh[kMaxK], nf = 0;
+    for (int q = 0; q < k; q++) {
+      const int i = want[q];
+      if (slot_of[i] >= 0) continue;
+      int pos = 0;
+      while (used[pos]) pos++;
+      used[pos] = true;
+      slot_of[i] = pos;
+      fresh[nf++] = i;
+      if (sfs > 0)
+        MEC_CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(s.aux.p) + pos * fpitch, files[i], static_cast<size_t>(sfs), cudaMemcpyHostToDevice, s.st));
+      c->st_h2d += sfs;
+    }
+    if (nf == 0) break;
+    for (int q = 0; q < nf; q++) {  // one launch per newcomer keeps the arena positions arbitrary; these files are few and the hash is serial anyway
+      const int pos = slot_of[fresh[q]];
+      if ((rc = whole_hash_device(c, c->algo, static_cast<const uint8_t*>(s.aux.p) + pos * fpitch, fpitch, sfs, 1,
+                                  static_cast<uint8_t*>(s.dig.p) + pos * 64, s.st)))
+        return rc;
+      c->eng->count_launch();
+    }
+    MEC_CUDA_OK(cudaMemcpyAsync(s.hdig.p, s.dig.p, static_cast<size_t>(k * 64), cudaMemcpyDeviceToHost, s.st));
+    MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+    bool dropped = false;
+    for (int q = 0; q < nf; q++) {
+      const int i = fresh[q], pos = slot_of[i];
+      if (memcmp(static_cast<const uint8_t*>(s.hdig.p) + pos * 64, sums + static_cast<size_t>(i) * 64, static_cast<size_t>(ds)) != 0) {
+        alive[i] = 0;                 // errFileCorrupt: the reader is gone for the rest of the call
+        if (corrupt) corrupt[i] = 1;
+        c->st_corrupt++;
+        slot_of[i] = -1;
+        dropped = true;
+      } else {
+        verified[i] = true;
+      }
+    }
+    if (!dropped) break;
+  }
+  // compact into ascending order: position t must hold the t-th chosen file (decode rows are defined on ascending indices)
+  int nch = 0;
+  for (int i = 0; i < n && nch < k; i++)
+    if (alive[i] && verified[i]) chosen[nch++] = i;
+  if (nch < k) return MEC_ERR_READ_QUORUM;
+  for (int t = 0; t < k; t++) chosen[t] = chosen[t] | (slot_of[chosen[t]] << 16);  // low 16 bits: shard index, high: arena position
+  return MEC_OK;
+}
+
+// launch the rebuild of `targets` over blocks [first, first + nb) of raw shard files (stride S between blocks, no frames)
+static int launch_whole_rebuild(mec_codec* c, Slot& s, const int* chosen, int64_t fpitch, int64_t S, int64_t last_len, int64_t first,
+                                int64_t nb, int64_t nblocks_file, const uint8_t* rows, int r, int64_t pitch) {
+  const int k = c->k;
+  FusedDesc d;
+  d.k = k; d.r = r; d.coef = rows; d.static_encode = false; d.contiguous = false; d.hash_outputs = false;
+  d.key = kMagicKey; d.out_pitch = pitch; d.in_block_stride = S; d.digests = nullptr;
+  const bool has_short = (first + nb == nblocks_file) && last_len != S;
+  const int64_t nfull = has_short ? nb - 1 : nb;
+  for (int pass = 0; pass < 2; pass++) {
+    const int64_t f0 = pass == 0 ? 0 : nfull, cnt = pass == 0 ? nfull : nb - nfull;
+    if (cnt <= 0) continue;
+    d.nblocks = cnt;
+    d.S = static_cast<int32_t>(pass == 0 ? S : last_len);
+    for (int t = 0; t < k; t++) {
+      const uint8_t* base = static_cast<const uint8_t*>(s.aux.p) + (chosen[t] >> 16) * fpitch;
+      d.in_ptr[t] = base + (first + f0) * S;
+      d.map_base[t] = base;
+      d.map_len[t] = fpitch;
+    }
+    d.out = static_cast<uint8_t*>(s.out.p) + f0 * r * pitch;
+    int rc = c->eng->launch_fused(d, c->opt, s.st);
+    if (rc) return rc;
+  }
+  return MEC_OK;
+}
+
+extern "C" int64_t mec_decode_whole(mec_codec* c, const uint8_t* const* files, const uint8_t* sums, int64_t offset, int64_t length,
+                                    int64_t total, uint8_t* dst, int* heal_hint) {
+  NvtxRange nvtx("mec_decode_whole");
+  if (heal_hint) *heal_hint = 0;
+  if (!c || !files || !sums) return MEC_ERR_INVALID_ARGUMENT;
+  if (offset < 0 || length < 0) return MEC_ERR_INVALID_ARGUMENT;      // cmd/erasure-decode.go:240-242
+  if (offset + length > total) return MEC_ERR_INVALID_ARGUMENT;       // :243-245
+  if (length == 0) return 0;                                          // :247-249
+  if (!dst) return MEC_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = require_whole(c);
+  if (rc) return rc;
+  const int k = c->k, n = c->n;
+  if (k > kMaxK || n > kMaxShards || c->S() >= (1ll << 31)) return MEC_ERR_UNSUPPORTED;
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  const int64_t bs = c->block_size, S = c->S(), sfs = mec_shard_file_size(c, total);
+  const int64_t nblocks_file = ceil_frac(sfs, S), last_len_file = sfs - (nblocks_file - 1) * S;
+  const int64_t start_block = offset / bs;
+  int64_t last_block = (offset + length) / bs;
+  if ((offset + length) % bs == 0) last_block--;
+  if (last_block >= nblocks_file) last_block = nblocks_file - 1;
+  const int64_t nb = last_block - start_block + 1;
+  Slot& s = c->slots[0];
+  struct Drain { Slot& s; ~Drain() { if (s.st) cudaStreamSynchronize(s.st); } } drain{s};
+  const int64_t fpitch = round_up(sfs, 16) + 256, pitch = round_up(S, 16);
+  std::vector<uint8_t> alive(n), corrupt(n, 0);
+  for (int i = 0; i < n; i++) alive[i] = files[i] != nullptr;
+  int chosen[kMaxShards];
+  if ((rc = stage_verified_whole(c, files, sums, sfs, alive.data(), corrupt.data(), chosen, fpitch, s))) return rc;
+  std::vector<uint8_t> present(n, 0);
+  for (int t = 0; t < k; t++) present[chosen[t] & 0xffff] = 1;
+  int targets[kMaxShards], r = 0;
+  for (int i = 0; i < k; i++)
+    if (!present[i]) targets[r++] = i;
+  if (r > kMaxR) return MEC_ERR_UNSUPPORTED;
+  std::vector<uint8_t> rows(static_cast<size_t>(std::max(r, 1)) * k);
+  int valid[kMaxShards];
+  if (r > 0 && !rs_decode_rows(k, c->m, present.data(), targets, r, rows.data(), valid)) return MEC_ERR_TOO_FEW_SHARDS;
+  if (r > 0) {
+    if ((rc = s.out.ensure(static_cast<size_t>(nb * r * pitch)))) return rc;
+    if ((rc = launch_whole_rebuild(c, s, chosen, fpitch, S, last_len_file, start_block, nb, nblocks_file, rows.data(), r, pitch))) return rc;
+  }
+  // writeDataBlocks by DMA: data shard i of block B sits in a verified shard file (stride S) or in a rebuilt row
+  for (int i = 0; i < k; i++) {
+    const uint8_t* base = nullptr;
+    int64_t spitch = 0;
+    for (int t = 0; t < k && !base; t++)
+      if ((chosen[t] & 0xffff) == i) { base = static_cast<const uint8_t*>(s.aux.p) + (chosen[t] >> 16) * fpitch + start_block * S; spitch = S; }
+    for (int q = 0; q < r && !base; q++)
+      if (targets[q] == i) { base = static_cast<const uint8_t*>(s.out.p) + q * pitch; spitch = r * pitch; }
+    if (!base) return MEC_ERR_UNEXPECTED;
+    for (int64_t b = 0; b < nb; b++) {
+      const int64_t B = start_block + b, blo = B * bs, bhi = std::min(blo + bs, total);
+      const int64_t cur = (B == nblocks_file - 1) ? last_len_file : S;
+      const int64_t slo = blo + static_cast<int64_t>(i) * cur, shi = std::min(slo + cur, bhi);
+      const int64_t a = std::max(slo, offset), e = std::min(shi, offset + length);
+      if (e > a) {
+        MEC_CUDA_OK(cudaMemcpyAsync(dst + (a - offset), base + b * spitch + (a - slo), static_cast<size_t>(e - a), cudaMemcpyDeviceToHost, s.st));
+        c->st_d2h += e - a;
+      }
+    }
+  }
+  MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+  c->st_blocks_read += nb;
+  c->st_shards_rebuilt += nb * r;
+  if (heal_hint)
+    for (int i = 0; i < n; i++)
+      if (corrupt[i]) *heal_hint = MEC_ERR_FILE_CORRUPT;
+  return length;
+}
+
+extern "C" int mec_heal_whole(mec_codec* c, const uint8_t* const* files, const uint8_t* sums, int64_t total,
+                              uint8_t* const* out_files, uint8_t* out_sums, uint8_t* corrupt_out) {
+  NvtxRange nvtx("mec_heal_whole");
+  if (!c || !files || !sums || !out_files) return MEC_ERR_INVALID_ARGUMENT;
+  if (corrupt_out) memset(corrupt_out, 0, static_cast<size_t>(c->n));
+  if (total <= 0) return MEC_OK;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = require_whole(c);
+  if (rc) return rc;
+  const int k = c->k, n = c->n;
+  if (k > kMaxK || n > kMaxShards || c->S() >= (1ll << 31)) return MEC_ERR_UNSUPPORTED;
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  const int64_t S = c->S(), sfs = mec_shard_file_size(c, total);
+  const int64_t nblocks = ceil_frac(sfs, S), last_len = sfs - (nblocks - 1) * S;
+  Slot& s = c->slots[0];
+  struct Drain { Slot& s; ~Drain() { if (s.st) cudaStreamSynchronize(s.st); } } drain{s};
+  const int64_t fpitch = round_up(sfs, 16) + 256, pitch = round_up(S, 16);
+  std::vector<uint8_t> alive(n), corrupt(n, 0);
+  for (int i = 0; i < n; i++) alive[i] = files[i] != nullptr;
+  int chosen[kMaxShards];
+  if ((rc = stage_verified_whole(c, files, sums, sfs, alive.data(), corrupt.data(), chosen, fpitch, s))) return rc;
+  std::vector<uint8_t> present(n, 0);
+  for (int t = 0; t < k; t++) present[chosen[t] & 0xffff] = 1;
+  int targets[kMaxShards], r = 0;
+  for (int i = 0; i < n; i++)
+    if (out_files[i] && !present[i]) targets[r++] = i;
+  if (r > kMaxR) return MEC_ERR_UNSUPPORTED;
+  if (r > 0) {
+    std::vector<uint8_t> rows(static_cast<size_t>(r) * k);
+    int valid[kMaxShards];
+    if (!rs_decode_rows(k, c->m, present.data(), targets, r, rows.data(), valid)) return MEC_ERR_TOO_FEW_SHARDS;
+    if ((rc = s.out.ensure(static_cast<size_t>(nblocks * r * pitch)))) return rc;
+    if ((rc = launch_whole_rebuild(c, s, chosen, fpitch, S, last_len, 0, nblocks, nblocks, rows.data(), r, pitch))) return rc;
+    // rebuilt rows -> contiguous shard files on the device (for the whole-file hash), then files and sums go home
+    if ((rc = s.src.ensure(static_cast<size_t>(r * fpitch + 256)))) return rc;
+    if ((rc = s.dig.ensure(static_cast<size_t>((k + r) * 64)))) return rc;
+    if ((rc = s.hdig.ensure(static_cast<size_t>((k + r) * 64)))) return rc;
+    for (int q = 0; q < r; q++) {
+      uint8_t* f = static_cast<uint8_t*>(s.src.p) + q * fpitch;
+      const int64_t nfull = last_len == S ? nblocks : nblocks - 1;
+      if (nfull > 0)
+        MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(S), static_cast<uint8_t*>(s.out.p) + q * pitch, static_cast<size_t>(r * pitch),
+                                      static_cast<size_t>(S), static_cast<size_t>(nfull), cudaMemcpyDeviceToDevice, s.st));
+      if (nfull < nblocks)
+        MEC_CUDA_OK(cudaMemcpyAsync(f + nfull * S, static_cast<uint8_t*>(s.out.p) + (nfull * r + q) * pitch, static_cast<size_t>(last_len),
+                                    cudaMemcpyDeviceToDevice, s.st));
+      MEC_CUDA_OK(cudaMemsetAsync(f + sfs, 0, 256, s.st));
+    }
+    if ((rc = whole_hash_device(c, c->algo, static_cast<const uint8_t*>(s.src.p), fpitch, sfs, r, static_cast<uint8_t*>(s.dig.p) + k * 64, s.st))) return rc;
+    c->eng->count_launch();
+    for (int q = 0; q < r; q++) {
+      MEC_CUDA_OK(cudaMemcpyAsync(out_files[targets[q]], static_cast<uint8_t*>(s.src.p) + q * fpitch, static_cast<size_t>(sfs), cudaMemcpyDeviceToHost, s.st));
+      if (out_sums)
+        MEC_CUDA_OK(cudaMemcpyAsync(out_sums + static_cast<size_t>(targets[q]) * 64, static_cast<uint8_t*>(s.dig.p) + (k + q) * 64, 64, cudaMemcpyDeviceToHost, s.st));
+      c->st_d2h += sfs;
+    }
+  }
+  // wanted shards that were read and verified are passed through
+  for (int i = 0; i < n; i++)
+    if (out_files[i] && present[i] && out_files[i] != files[i]) {
+      memcpy(out_files[i], files[i], static_cast<size_t>(sfs));
+      if (out_sums) memcpy(out_sums + static_cast<size_t>(i) * 64, sums + static_cast<size_t>(i) * 64, 64);
+    }
+  MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+  c->st_blocks_read += nblocks;
+  c->st_shards_rebuilt += nblocks * r;
+  bool any = false;
+  for (int i = 0; i < n; i++) { any |= corrupt[i] != 0; if (corrupt_out) corrupt_out[i] = corrupt[i]; }
+  return any ? MEC_ERR_FILE_CORRUPT : MEC_OK;  // Heal's derr (cmd/erasure-decode.go:338-341,366)
+}
+
+// ------------------------------------------------------------------------------------------------
 // shard-shaped low level calls
 static int apply_rows_host(mec_codec* c, const uint8_t* rows, int r, const uint8_t* const* in, uint8_t* const* outp,
                            int64_t len, bool is_encode) {
@@ -1285,6 +1535,31 @@ extern "C" int mec_selftest(int device) {
     }
     mec_codec_free(c);
     if (memcmp(sum, want, 32) != 0) { set_last_error("bitrot self-test mismatch"); return MEC_ERR_UNEXPECTED; }
+  }
+  // the whole-file algorithms of the same self test (cmd/bitrot.go:225-229): Size()*BlockSize() bytes, Size() at a time
+  {
+    static const struct { int algo, size, block; const char* want; } kChains[] = {
+        {MEC_SHA256, 32, 64, "a7677ff19e0182e4d52e3a3db727804abc82a5818749336369552e54b838b004"},
+        {MEC_BLAKE2B512, 64, 128, "e519b7d84b1c3c917985f544773a35cf265dcab10948be3550320d156bab612124a5ae2ae5a8c73c0eea360f68b0e28136f26e858756dbfe7375a7389f26c669"},
+        {MEC_HIGHWAYHASH256, 32, 32, "39c0407ed3f01b18d22c85db4aeff11e060ca5f43131b0126731ca197cd42313"}};
+    for (const auto& ch : kChains) {
+      mec_codec* c = nullptr;
+      int rc = mec_codec_new(2, 2, 1 << 20, ch.algo, device, &c);
+      if (rc) return rc;
+      std::vector<uint8_t> msg;
+      uint8_t sum[64];
+      for (int i = 0; i < ch.size * ch.block; i += ch.size) {
+        rc = mec_whole_hash(c, ch.algo, msg.data(), static_cast<int64_t>(msg.size()), 1, sum);
+        if (rc) { mec_codec_free(c); return rc; }
+        msg.insert(msg.end(), sum, sum + ch.size);
+      }
+      mec_codec_free(c);
+      for (int i = 0; i < ch.size; i++) {
+        unsigned v = 0;
+        sscanf(ch.want + 2 * i, "%2x", &v);
+        if (sum[i] != v) { set_last_error("bitrot self-test mismatch (whole-file algorithm " + std::to_string(ch.algo) + ")"); return MEC_ERR_UNEXPECTED; }
+      }
+    }
   }
   return MEC_OK;
 }

@@ -210,3 +210,100 @@ def test_group_claiming_modes_agree(mb, oracle, static_groups):
     # every block was written exactly once: no digest row is left zero
     assert bool((dig.view(torch.int64).reshape(nblocks, -1) != 0).any(dim=1).all().item())
     c.close()
+
+
+# cmd/erasure-decode_test.go:44-83, all 38 rows: (dataBlocks, onDisks, offDisks, blocksize, data, offset, length, algorithm,
+# shouldFail, shouldFailQuorum).  DefaultBitrotAlgorithm = HighwayHash256S (streaming frames); BLAKE2b512 / SHA256 = whole-file
+# readers.  First pass: every drive online.  Second pass (only when the first may pass): the first offDisks drives fail
+# (badDisk) and reader 0 is nil — here both are "offline".
+H, B2, SH = "HighwayHash256S", "BLAKE2b512", "SHA256"
+DECODE_TABLE_FULL = [
+    (2, 4, 0, MiB, MiB, 0, MiB, B2, False, False), (3, 6, 0, MiB, MiB, 0, MiB, SH, False, False), (4, 8, 0, MiB, MiB, 0, MiB, H, False, False),
+    (5, 10, 0, MiB, MiB, 1, MiB - 1, B2, False, False), (6, 12, 0, MiB, MiB, MiB, 0, B2, False, False), (7, 14, 0, MiB, MiB, 3, 1024, H, False, False),
+    (8, 16, 0, MiB, MiB, 4, 8 * 1024, H, False, False), (7, 14, 7, MiB, MiB, MiB, 1, H, True, False), (6, 12, 6, MiB, MiB, 0, MiB, H, False, False),
+    (5, 10, 5, MiB, MiB, 0, MiB, B2, False, False), (4, 8, 4, MiB, MiB, 0, MiB, SH, False, False), (3, 6, 3, MiB, MiB, 0, MiB, H, False, False),
+    (2, 4, 2, MiB, MiB, 0, MiB, H, False, False), (2, 4, 1, MiB, MiB, 0, MiB, H, False, False), (3, 6, 2, MiB, MiB, 0, MiB, H, False, False),
+    (4, 8, 3, 2 * MiB, MiB, 0, MiB, H, False, False), (5, 10, 6, MiB, MiB, 0, MiB, H, False, True), (5, 10, 2, MiB, 2 * MiB, MiB, MiB, H, False, False),
+    (5, 10, 1, MiB, MiB, 0, MiB, B2, False, False), (6, 12, 3, MiB, MiB, 0, MiB, SH, False, False), (6, 12, 7, MiB, MiB, 0, MiB, H, False, True),
+    (8, 16, 8, MiB, MiB, 0, MiB, H, False, False), (8, 16, 9, MiB, MiB, 0, MiB, H, False, True), (8, 16, 7, MiB, MiB, 0, MiB, H, False, False),
+    (2, 4, 1, MiB, MiB, 0, MiB, H, False, False), (2, 4, 0, MiB, MiB, 0, MiB, H, False, False), (2, 4, 0, MiB, MiB + 1, 0, MiB + 1, B2, False, False),
+    (2, 4, 0, MiB, 2 * MiB, 12, MiB + 17, B2, False, False), (3, 6, 0, MiB, 2 * MiB, 1023, MiB + 1024, H, False, False),
+    (4, 8, 0, MiB, 2 * MiB, 11, MiB + 2 * 1024, H, False, False), (6, 12, 0, MiB, 2 * MiB, 512, MiB + 8 * 1024, H, False, False),
+    (8, 16, 0, MiB, 2 * MiB, MiB, MiB - 1, H, False, False), (2, 4, 0, MiB, MiB, -1, 3, H, True, False), (2, 4, 0, MiB, MiB, 1024, -1, H, True, False),
+    (4, 6, 0, MiB, MiB, 0, MiB, B2, False, False), (4, 6, 1, MiB, 2 * MiB, 12, MiB + 17, B2, False, False),
+    (4, 6, 3, MiB, 2 * MiB, 1023, MiB + 1024, H, False, True), (8, 12, 4, MiB, 2 * MiB, 11, MiB + 2 * 1024, H, False, False),
+]
+
+
+@pytest.mark.parametrize("row", range(len(DECODE_TABLE_FULL)))
+def test_erasure_decode_full_table(mb, oracle, row):
+    k, n, off, bs, size, offset, length, algo, should_fail, should_fail_quorum = DECODE_TABLE_FULL[row]
+    m = n - k
+    data = rand(size, 1000 + row)
+    whole = algo != H
+    if whole:
+        code = {B2: mb.BLAKE2B512, SH: mb.SHA256}[algo]
+        c = mb.Codec(k, m, bs, algo=code)
+        files, sums = c.encode_whole(data)
+        ofiles, osums = oracle.erasure_encode(k, m, bs, {B2: oracle.BLAKE2B512, SH: oracle.SHA256}[algo], data)
+        for i in range(n):
+            assert np.array_equal(files[i], ofiles[i]) and sums[i] == osums[i]
+        run = lambda fl: c.decode_whole(fl, sums, offset, length, size)
+    else:
+        c = mb.Codec(k, m, bs)
+        files = c.encode(data)
+        run = lambda fl: c.decode(fl, offset, length, size)
+    try:
+        out, hint = run(files)
+        assert not should_fail, "should fail but it passed"
+        assert hint == 0 and np.array_equal(out, data[offset:offset + length])
+    except mb.MecError as e:
+        assert should_fail, f"should pass but failed with {e}"
+        c.close()
+        return
+    fl = [None if (j < off or (off > 0 and j == 0)) else files[j] for j in range(n)]
+    try:
+        out, hint = run(fl)
+        assert not should_fail_quorum, "should fail with a quorum error but it passed"
+        assert np.array_equal(out, data[offset:offset + length])
+    except mb.MecError as e:
+        assert should_fail_quorum and e.code == -10, f"should pass but failed with {e}"
+    c.close()
+
+
+@pytest.mark.parametrize("algo", ["SHA256", "BLAKE2b512", "HighwayHash256"])
+def test_whole_file_decode_and_heal_with_bitrot(mb, oracle, algo):
+    """wholeBitrotReader: a shard file whose whole-file digest is wrong is errFileCorrupt — dropped, replaced by the next drive,
+    reported; Heal rebuilds stale shard files and their sums and still returns the side-band error."""
+    code = {"SHA256": mb.SHA256, "BLAKE2b512": mb.BLAKE2B512, "HighwayHash256": mb.HIGHWAYHASH256}[algo]
+    k, m, bs, size = 6, 4, MiB, 5 * MiB + 777
+    n = k + m
+    data = rand(size, 4242)
+    c = mb.Codec(k, m, bs, algo=code)
+    files, sums = c.encode_whole(data)
+    bad = [f.copy() for f in files]
+    bad[1][12345] ^= 0x20
+    bad[7][0] ^= 0x01
+    srcs = [None if i in (0, 3) else bad[i] for i in range(n)]        # readers 1,2,4,5,6,7 first; 1 and 7 are corrupt -> 8, 9 step in
+    out, hint = c.decode_whole(srcs, sums, 3, size - 10, size)
+    assert hint == -7 and np.array_equal(out, data[3:size - 7])
+    out, hint = c.decode_whole([None if i in (0, 3) else files[i] for i in range(n)], sums, 0, size, size)
+    assert hint == 0 and np.array_equal(out, data)
+    stale = [i in (0, 9) for i in range(n)]
+    srcs = [None if stale[i] else bad[i] for i in range(n)]
+    outs, osums, rc, corrupt = c.heal_whole(srcs, sums, stale, size)
+    assert rc == -7 and list(np.nonzero(corrupt)[0]) == [1, 7]         # readers 1..6 first: 1 drops, 7 steps in and drops, 8 steps in
+    for i in (0, 9):
+        assert np.array_equal(outs[i], files[i]) and osums[i] == sums[i]
+    stale = [i in (0, 3, 9) for i in range(n)]
+    outs, osums, rc, corrupt = c.heal_whole([None if stale[i] else files[i] for i in range(n)], sums, stale, size)
+    assert rc == 0 and not corrupt.any()
+    for i in (0, 3, 9):
+        assert np.array_equal(outs[i], files[i]) and osums[i] == sums[i]
+    # too many corrupt files: read quorum
+    for i in (2, 4, 5, 6):
+        bad[i][99] ^= 0xFF
+    with pytest.raises(mb.MecError) as ei:
+        c.decode_whole([None if i in (0, 3) else bad[i] for i in range(n)], sums, 0, size, size)
+    assert ei.value.code == -10
+    c.close()
