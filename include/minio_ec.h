@@ -172,6 +172,23 @@ int mec_heal_prefer(mec_codec* c, const uint8_t* const* files, const uint8_t* pr
 int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobjects, const uint8_t* const* const* files,
                    const int64_t* total_lengths, uint8_t* const* const* out_files, int* rcs);
 
+/* ---- object checksums of the PutObject stream (internal/hash/checksum.go:64-73, internal/hash/crc.go) ---------------------
+ * CRC32 (IEEE), CRC32C (Castagnoli) and CRC64NVME — the checksum types hash.Reader can merge (ChecksumType.CanMerge) — of a
+ * byte stream, as the finalized values Go's hash/crc32 and hash/crc64 return (big-endian encode them for Checksum.Raw).
+ * `which` is a mask of MEC_CRC*; out3[0] = CRC32, out3[1] = CRC32C, out3[2] = CRC64NVME (0 where not asked for).
+ *   mec_checksums_device : the stream is already in device memory (e.g. staged for an encode)
+ *   mec_checksums        : host buffer, staged through the codec's slots
+ *   mec_checksum_combine : Checksum.AddPart (crc.go:32-73): checksum of A || B from those of A and B and |B|, on the host
+ * mec_set_option(c, "checksums", mask) makes mec_encode / mec_encode_sg / mec_encode_blocks compute them on the bytes they stage
+ * anyway (the object crosses PCIe once); mec_last_checksums returns the values of the codec's last such call and its length. */
+#define MEC_CRC32 1
+#define MEC_CRC32C 2
+#define MEC_CRC64NVME 4
+int mec_checksums_device(mec_codec* c, const uint8_t* d_src, int64_t len, int which, uint64_t* out3, void* cuda_stream);
+int mec_checksums(mec_codec* c, const uint8_t* src, int64_t len, int which, uint64_t* out3);
+uint64_t mec_checksum_combine(int type, uint64_t crc1, uint64_t crc2, int64_t len2);
+int64_t mec_last_checksums(const mec_codec* c, uint64_t* out3);
+
 /* ---- legacy whole-file bitrot (cmd/bitrot-whole.go, BitrotAlgorithm SHA256 / BLAKE2b512 / HighwayHash256) ----
  * Erasure.Encode with wholeBitrotWriters (cmd/bitrot-whole.go:35-45): files[i] receives the raw shard file
  * (shards of all blocks back to back, mec_shard_file_size(len) bytes) and sums + i*64 the digest over the whole

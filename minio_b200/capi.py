@@ -59,6 +59,12 @@ def lib():
     L.mec_encode_sg.restype = i64
     L.mec_encode_sg.argtypes = [vp, vp, i64, vp, vp, i32]
     L.mec_heal_prefer.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.mec_checksums.argtypes = [vp, vp, i64, i32, vp]
+    L.mec_checksums_device.argtypes = [vp, vp, i64, i32, vp, vp]
+    L.mec_checksum_combine.restype = C.c_uint64
+    L.mec_checksum_combine.argtypes = [i32, C.c_uint64, C.c_uint64, i64]
+    L.mec_last_checksums.restype = i64
+    L.mec_last_checksums.argtypes = [vp, vp]
     L.mec_decode_whole.restype = i64
     L.mec_decode_whole.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
     L.mec_heal_whole.argtypes = [vp, vp, vp, i64, vp, vp, vp]
@@ -211,6 +217,27 @@ class Codec:
         if rc < 0:
             raise MecError(rc, "mec_encode_sg")
         return [f if i >= self.k else None for i, f in enumerate(files)], dd[:nb]
+
+    def checksums(self, data, which=7):
+        """-> (CRC32, CRC32C, CRC64NVME) of a host byte string (mec_checksums); 0 where not asked for."""
+        d = _u8(data)
+        out = (C.c_uint64 * 3)()
+        rc = lib().mec_checksums(self.h, d.ctypes.data if d.size else None, d.size, which, out)
+        if rc:
+            raise MecError(rc, "mec_checksums")
+        return tuple(int(v) for v in out)
+
+    def checksums_device(self, d_src, length, which=7, stream=0):
+        out = (C.c_uint64 * 3)()
+        rc = lib().mec_checksums_device(self.h, d_src, length, which, out, stream)
+        if rc:
+            raise MecError(rc, "mec_checksums_device")
+        return tuple(int(v) for v in out)
+
+    def last_checksums(self):
+        out = (C.c_uint64 * 3)()
+        n = lib().mec_last_checksums(self.h, out)
+        return tuple(int(v) for v in out), n
 
     def stat(self, name):
         return lib().mec_get_stat(self.h, name.encode())

@@ -14,6 +14,7 @@
 #include "../../include/minio_ec.h"
 #include "ec_engine.h"
 #include "whole_hash.cuh"
+#include "crc.cuh"
 #include <nvtx3/nvToolsExt.h>
 
 struct NvtxRange {
@@ -59,7 +60,8 @@ struct PinBuf {
 
 struct Slot {
   DevBuf src, out, dig, aux, flags;  // aux: survivor arena of a reconstruct chunk / shard files of the whole-file path
-  PinBuf hdig, hflags;
+  DevBuf crc_part, crc_out;          // object checksums of an encode chunk (crc.cuh)
+  PinBuf hdig, hflags, hcrc;
   cudaStream_t st = nullptr;
 };
 
@@ -72,7 +74,11 @@ struct mec_codec {
   EngineOptions opt;
   std::mutex mu;
   Slot slots[kSlots];
-  DevBuf flags;
+  DevBuf flags, crc_tables;
+  std::unique_ptr<CrcTables> crc_host;  // host copy of the CRC tables (combine across chunks)
+  int checksums = 0;                    // option "checksums": MEC_CRC32 | MEC_CRC32C | MEC_CRC64NVME computed by the host-buffer encode calls
+  uint64_t last_crc[kCrcTypes] = {0, 0, 0};
+  int64_t last_crc_len = 0;
   // boundary counters (mec_get_stat)
   int64_t st_blocks_encoded = 0, st_blocks_read = 0, st_shards_rebuilt = 0, st_corrupt = 0, st_h2d = 0, st_d2h = 0;
   int64_t S() const { return ceil_frac(block_size, k); }
@@ -155,9 +161,10 @@ extern "C" void mec_codec_free(mec_codec* c) {
   for (auto& s : c->slots) {
     if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
     s.src.release(); s.out.release(); s.dig.release(); s.aux.release(); s.flags.release();
-    s.hdig.release(); s.hflags.release();
+    s.hdig.release(); s.hflags.release(); s.hcrc.release(); s.crc_part.release(); s.crc_out.release();
   }
   c->flags.release();
+  c->crc_tables.release();
   delete c;
 }
 
@@ -174,6 +181,7 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else if (!strcmp(name, "no_rows3d")) c->opt.no_rows3d = static_cast<int>(v);
   else if (!strcmp(name, "chunk_blocks")) c->opt.chunk_blocks = v;
   else if (!strcmp(name, "static_groups")) c->opt.static_groups = static_cast<int>(v);
+  else if (!strcmp(name, "checksums")) c->checksums = static_cast<int>(v) & 7;
   else return MEC_ERR_INVALID_ARGUMENT;
   return MEC_OK;
 }
@@ -207,6 +215,116 @@ static int require_streaming(mec_codec* c) {
   }
   std::lock_guard<std::mutex> lk(c->mu);
   return ensure_engine(c);
+}
+
+// ------------------------------------------------------------------------------------------------
+// object checksums (internal/hash/checksum.go, crc.go): CRC32 / CRC32C / CRC64NVME of a byte stream that is already in HBM
+static int ensure_crc(mec_codec* c) {
+  if (c->crc_host) return MEC_OK;
+  std::unique_ptr<CrcTables> t(new CrcTables);
+  crc_build_tables(t.get());
+  int rc = c->crc_tables.ensure(sizeof(CrcTables));
+  if (rc) return rc;
+  MEC_CUDA_OK(cudaMemcpy(c->crc_tables.p, t.get(), sizeof(CrcTables), cudaMemcpyHostToDevice));
+  c->crc_host = std::move(t);
+  return MEC_OK;
+}
+// enqueue: CRCs of d_src[0, len) -> d_out3 (device, kCrcTypes words); `part` is scratch for the per-region partials
+static int checksums_enqueue(mec_codec* c, const uint8_t* d_src, int64_t len, int which, DevBuf& part, uint64_t* d_out3, cudaStream_t st) {
+  int rc = ensure_crc(c);
+  if (rc) return rc;
+  CrcParams p;
+  p.src = d_src; p.len = len; p.which = which & 7;
+  p.tables = static_cast<const CrcTables*>(c->crc_tables.p);
+  p.nregions = (len + kCrcRegion - 1) / kCrcRegion;
+  if ((rc = part.ensure(static_cast<size_t>(std::max<int64_t>(p.nregions, 1)) * kCrcTypes * sizeof(uint64_t)))) return rc;
+  p.partial = static_cast<uint64_t*>(part.p);
+  p.out = d_out3;
+  if (p.nregions > 0) {
+    const unsigned grid = static_cast<unsigned>(std::min<int64_t>(p.nregions, static_cast<int64_t>(c->eng->num_sms()) * 8));
+    crc_regions_kernel<<<grid, kCrcThreads, 0, st>>>(p);
+    MEC_CUDA_OK(cudaGetLastError());
+    c->eng->count_launch();
+  }
+  crc_fold_kernel<<<1, kCrcThreads, 0, st>>>(p);
+  MEC_CUDA_OK(cudaGetLastError());
+  c->eng->count_launch();
+  return MEC_OK;
+}
+
+extern "C" uint64_t mec_checksum_combine(int type, uint64_t crc1, uint64_t crc2, int64_t len2) {
+  const int ty = type == MEC_CRC32 ? 0 : (type == MEC_CRC32C ? 1 : (type == MEC_CRC64NVME ? 2 : -1));
+  if (ty < 0) return 0;
+  static const CrcTables* tabs = [] { CrcTables* t = new CrcTables; crc_build_tables(t); return t; }();
+  const CrcSpec sp = crc_spec(ty);
+  return crc_combine(tabs->xp8[ty], crc1, crc2, len2, sp.poly, sp.bits);  // Checksum.AddPart (internal/hash/crc.go:32-73)
+}
+
+extern "C" int mec_checksums_device(mec_codec* c, const uint8_t* d_src, int64_t len, int which, uint64_t* out3, void* stream) {
+  if (!c || len < 0 || !out3 || (len > 0 && !d_src)) return MEC_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = ensure_engine(c);
+  if (rc) return rc;
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  Slot& s = c->slots[0];
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((rc = s.crc_out.ensure(kCrcTypes * sizeof(uint64_t)))) return rc;
+  if ((rc = checksums_enqueue(c, d_src, len, which, s.crc_part, static_cast<uint64_t*>(s.crc_out.p), st))) return rc;
+  MEC_CUDA_OK(cudaMemcpyAsync(out3, s.crc_out.p, kCrcTypes * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+  MEC_CUDA_OK(cudaStreamSynchronize(st));
+  return MEC_OK;
+}
+
+extern "C" int mec_checksums(mec_codec* c, const uint8_t* src, int64_t len, int which, uint64_t* out3) {
+  if (!c || len < 0 || !out3 || (len > 0 && !src)) return MEC_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = ensure_engine(c);
+  if (rc) return rc;
+  if ((rc = ensure_crc(c))) return rc;
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  struct Drain { mec_codec* c; ~Drain() { for (auto& s : c->slots) if (s.st) cudaStreamSynchronize(s.st); } } drain{c};
+  const int64_t chunk = 64ll << 20;
+  uint64_t acc[kCrcTypes] = {0, 0, 0};
+  int64_t done = 0;
+  int64_t clen[kSlots] = {};
+  bool busy[kSlots] = {};
+  auto retire = [&](int si) {
+    const uint64_t* h = static_cast<const uint64_t*>(c->slots[si].hcrc.p);
+    for (int ty = 0; ty < kCrcTypes; ty++) {
+      const CrcSpec sp = crc_spec(ty);
+      acc[ty] = done == 0 ? h[ty] : crc_combine(c->crc_host->xp8[ty], acc[ty], h[ty], clen[si], sp.poly, sp.bits);
+    }
+    done += clen[si];
+    busy[si] = false;
+  };
+  int si = 0;
+  for (int64_t off = 0; off < len; off += chunk, si = (si + 1) % kSlots) {
+    Slot& s = c->slots[si];
+    MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+    if (busy[si]) retire(si);
+    const int64_t n = std::min(chunk, len - off);
+    if ((rc = s.src.ensure(static_cast<size_t>(round_up(n, 16) + 256)))) return rc;
+    if ((rc = s.crc_out.ensure(kCrcTypes * sizeof(uint64_t)))) return rc;
+    if ((rc = s.hcrc.ensure(kCrcTypes * sizeof(uint64_t)))) return rc;
+    MEC_CUDA_OK(cudaMemcpyAsync(s.src.p, src + off, static_cast<size_t>(n), cudaMemcpyHostToDevice, s.st));
+    if ((rc = checksums_enqueue(c, static_cast<const uint8_t*>(s.src.p), n, which, s.crc_part, static_cast<uint64_t*>(s.crc_out.p), s.st))) return rc;
+    MEC_CUDA_OK(cudaMemcpyAsync(s.hcrc.p, s.crc_out.p, kCrcTypes * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+    clen[si] = n;
+    busy[si] = true;
+    c->st_h2d += n;
+  }
+  for (int q = 0; q < kSlots; q++, si = (si + 1) % kSlots) {
+    MEC_CUDA_OK(cudaStreamSynchronize(c->slots[si].st));
+    if (busy[si]) retire(si);
+  }
+  for (int ty = 0; ty < kCrcTypes; ty++) out3[ty] = (which & (1 << ty)) ? acc[ty] : 0;
+  return MEC_OK;
+}
+
+extern "C" int64_t mec_last_checksums(const mec_codec* c, uint64_t* out3) {
+  if (!c || !out3) return MEC_ERR_INVALID_ARGUMENT;
+  for (int ty = 0; ty < kCrcTypes; ty++) out3[ty] = c->last_crc[ty];
+  return c->last_crc_len;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -288,10 +406,30 @@ static int encode_pipeline(mec_codec* c, const uint8_t* src, int64_t len, Enqueu
   EncChunk inflight[kSlots];
   bool busy[kSlots] = {};
   int si = 0, rc;
+  // option "checksums": CRCs of the object bytes ride along — computed on the chunk that was just staged for the encode (the
+  // bytes cross PCIe once), merged across chunks on the host the way Checksum.AddPart merges parts
+  const int ck = c->checksums;
+  int64_t ck_len[kSlots] = {}, ck_done = 0;
+  if (ck) {
+    if ((rc = ensure_crc(c))) return rc;
+    for (auto& v : c->last_crc) v = 0;
+    c->last_crc_len = 0;
+  }
+  auto ck_retire = [&](int q) {
+    if (!ck) return;
+    const uint64_t* h = static_cast<const uint64_t*>(c->slots[q].hcrc.p);
+    for (int ty = 0; ty < kCrcTypes; ty++) {
+      if (!(ck & (1 << ty))) continue;
+      const CrcSpec sp = crc_spec(ty);
+      c->last_crc[ty] = ck_done == 0 ? h[ty] : crc_combine(c->crc_host->xp8[ty], c->last_crc[ty], h[ty], ck_len[q], sp.poly, sp.bits);
+    }
+    ck_done += ck_len[q];
+    c->last_crc_len = ck_done;
+  };
   for (int64_t b0 = 0; b0 < nall; b0 += chunk, si = (si + 1) % kSlots) {
     Slot& s = c->slots[si];
     MEC_CUDA_OK(cudaStreamSynchronize(s.st));
-    if (busy[si]) { retire(inflight[si]); busy[si] = false; }
+    if (busy[si]) { ck_retire(si); retire(inflight[si]); busy[si] = false; }
     EncChunk ch;
     ch.b0 = b0; ch.nb = std::min(chunk, nall - b0); ch.s = &s; ch.pitch = pitch;
     const int64_t off = b0 * bs, bytes = std::min(len - off, ch.nb * bs);
@@ -303,13 +441,20 @@ static int encode_pipeline(mec_codec* c, const uint8_t* src, int64_t len, Enqueu
     if ((rc = encode_device_locked(c, static_cast<const uint8_t*>(s.src.p), bytes, static_cast<uint8_t*>(s.out.p), pitch,
                                    static_cast<uint8_t*>(s.dig.p), s.st)))
       return rc;
+    if (ck) {
+      if ((rc = s.crc_out.ensure(kCrcTypes * sizeof(uint64_t)))) return rc;
+      if ((rc = s.hcrc.ensure(kCrcTypes * sizeof(uint64_t)))) return rc;
+      if ((rc = checksums_enqueue(c, static_cast<const uint8_t*>(s.src.p), bytes, ck, s.crc_part, static_cast<uint64_t*>(s.crc_out.p), s.st))) return rc;
+      MEC_CUDA_OK(cudaMemcpyAsync(s.hcrc.p, s.crc_out.p, kCrcTypes * sizeof(uint64_t), cudaMemcpyDeviceToHost, s.st));
+      ck_len[si] = bytes;
+    }
     if ((rc = enqueue(ch))) return rc;
     inflight[si] = ch;
     busy[si] = true;
   }
   for (int q = 0; q < kSlots; q++, si = (si + 1) % kSlots) {  // oldest first
     MEC_CUDA_OK(cudaStreamSynchronize(c->slots[si].st));
-    if (busy[si]) { retire(inflight[si]); busy[si] = false; }
+    if (busy[si]) { ck_retire(si); retire(inflight[si]); busy[si] = false; }
   }
   c->st_blocks_encoded += nall;
   c->st_h2d += len;

@@ -205,3 +205,20 @@ int orc_bitrot_hash(int algo, const uint8_t *p, size_t n, uint8_t *out) {
   }
   return -1;
 }
+
+/* ---- object checksums (internal/hash/checksum.go:64-73): CRC32 (IEEE), CRC32C (Castagnoli), CRC64NVME ------------------
+ * Go's hash/crc32 and hash/crc64 (crc64.MakeTable(bits.Reverse64(0xad93d23594c93659)), internal/hash/crc.go:74-76): reflected,
+ * init and xorout all ones.  Bit-at-a-time restatement; pinned by the catalogue check values of "123456789"
+ * (0xCBF43926, 0xE3069283, 0xAE8B14860A799888) and zlib in tests/test_checksums.py. */
+static uint64_t crc_bits(const uint8_t *p, size_t n, uint64_t poly, int bits) {
+  const uint64_t mask = bits == 64 ? ~0ull : ((1ull << bits) - 1);
+  uint64_t c = mask;
+  for (size_t i = 0; i < n; i++) {
+    c ^= p[i];
+    for (int k = 0; k < 8; k++) c = (c & 1) ? (c >> 1) ^ poly : c >> 1;
+  }
+  return (c ^ mask) & mask;
+}
+uint64_t orc_crc32(const uint8_t *p, size_t n) { return crc_bits(p, n, 0xEDB88320ull, 32); }
+uint64_t orc_crc32c(const uint8_t *p, size_t n) { return crc_bits(p, n, 0x82F63B78ull, 32); }
+uint64_t orc_crc64nvme(const uint8_t *p, size_t n) { return crc_bits(p, n, 0x9A6C9329AC4BC9B5ull, 64); }

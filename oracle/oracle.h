@@ -141,6 +141,11 @@ double orc_encode_hash_blocks_mt(int k, int m, int64_t block_size, const uint8_t
  * worker that encodes it): orc_pool_fill writes synthetic bytes into src (nblocks * block_size) and clears the outputs;
  * orc_pool_encode_hash runs `reps` passes of SIMD RS encode + HighwayHash of every shard and returns the seconds between
  * releasing the workers and the last one finishing. */
+/* object checksums (internal/hash/checksum.go): finalized CRC values as Go's hash/crc32, hash/crc64 return them */
+uint64_t orc_crc32(const uint8_t *p, size_t n);
+uint64_t orc_crc32c(const uint8_t *p, size_t n);
+uint64_t orc_crc64nvme(const uint8_t *p, size_t n);
+
 typedef struct orc_pool orc_pool;
 orc_pool *orc_pool_new(int threads);
 void orc_pool_fill(orc_pool *p, int k, int m, int64_t block_size, uint8_t *src, int64_t nblocks, uint8_t *parity, uint8_t *digests, uint64_t seed);

@@ -67,6 +67,9 @@ def lib():
     L.orc_rs_encode_fast.restype = None
     L.orc_encode_hash_blocks_mt.restype = C.c_double
     L.orc_encode_hash_blocks_mt.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    for f in ("orc_crc32", "orc_crc32c", "orc_crc64nvme"):
+        getattr(L, f).restype = C.c_uint64
+        getattr(L, f).argtypes = [C.c_void_p, C.c_size_t]
     L.orc_pool_new.restype = C.c_void_p
     L.orc_pool_new.argtypes = [C.c_int]
     L.orc_pool_free.argtypes = [C.c_void_p]
@@ -251,3 +254,9 @@ def erasure_heal(k, m, bs, algo, files, avail, stale, total):
     st = np.asarray(stale, dtype=np.uint8)
     rc = lib().orc_erasure_heal(k, m, bs, algo, pa, av.ctypes.data, st.ctypes.data, total, po)
     return rc, outs
+
+
+def crcs(data):
+    """(CRC32, CRC32C, CRC64NVME) of a byte string, as Go's hash/crc32 / hash/crc64 return them."""
+    a = _buf(data)
+    return (lib().orc_crc32(_ptr(a), a.size), lib().orc_crc32c(_ptr(a), a.size), lib().orc_crc64nvme(_ptr(a), a.size))
