@@ -172,6 +172,22 @@ int mec_heal_prefer(mec_codec* c, const uint8_t* const* files, const uint8_t* pr
 int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobjects, const uint8_t* const* const* files,
                    const int64_t* total_lengths, uint8_t* const* const* out_files, int* rcs);
 
+/* ---- cross-request coalescer: many concurrent PutObject calls, one launch ---------------------------------------------------
+ * MinIO encodes one block per loop iteration on every request goroutine (cmd/erasure-encode.go:76-108, one Erasure per request,
+ * cmd/erasure-object.go:1371); a launch that small leaves 147 of 148 SMs idle.  A batcher owns one codec (k, m, block_size,
+ * HighwayHash256S) and a worker thread: callers block in mec_batcher_encode / mec_batcher_encode_sg (same arguments and results
+ * as mec_encode / mec_encode_sg), the worker merges everything that is queued — up to max_batch_blocks erasure blocks, waiting
+ * at most max_wait_us for company when the GPU is idle — into one staged buffer and ONE fused launch over all full blocks, then
+ * DMA-copies every caller's frames straight into that caller's buffers.  Up to three merged batches are in flight.
+ * mec_batcher_stat: "batches", "requests", "blocks", "launches". */
+typedef struct mec_batcher mec_batcher;
+int mec_batcher_new(int k, int m, int64_t block_size, int device, int64_t max_batch_blocks, int max_wait_us, mec_batcher** out);
+void mec_batcher_free(mec_batcher* b);
+int64_t mec_batcher_encode(mec_batcher* b, const uint8_t* src, int64_t len, uint8_t* const* files, int write_quorum);
+int64_t mec_batcher_encode_sg(mec_batcher* b, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* data_digests,
+                              int write_quorum);
+int64_t mec_batcher_stat(const mec_batcher* b, const char* name);
+
 /* ---- object checksums of the PutObject stream (internal/hash/checksum.go:64-73, internal/hash/crc.go) ---------------------
  * CRC32 (IEEE), CRC32C (Castagnoli) and CRC64NVME — the checksum types hash.Reader can merge (ChecksumType.CanMerge) — of a
  * byte stream, as the finalized values Go's hash/crc32 and hash/crc64 return (big-endian encode them for Checksum.Raw).

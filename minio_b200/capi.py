@@ -59,6 +59,15 @@ def lib():
     L.mec_encode_sg.restype = i64
     L.mec_encode_sg.argtypes = [vp, vp, i64, vp, vp, i32]
     L.mec_heal_prefer.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.mec_batcher_new.argtypes = [i32, i32, i64, i32, i64, i32, C.POINTER(vp)]
+    L.mec_batcher_free.argtypes = [vp]
+    L.mec_batcher_free.restype = None
+    L.mec_batcher_encode.restype = i64
+    L.mec_batcher_encode.argtypes = [vp, vp, i64, vp, i32]
+    L.mec_batcher_encode_sg.restype = i64
+    L.mec_batcher_encode_sg.argtypes = [vp, vp, i64, vp, vp, i32]
+    L.mec_batcher_stat.restype = i64
+    L.mec_batcher_stat.argtypes = [vp, C.c_char_p]
     L.mec_checksums.argtypes = [vp, vp, i64, i32, vp]
     L.mec_checksums_device.argtypes = [vp, vp, i64, i32, vp, vp]
     L.mec_checksum_combine.restype = C.c_uint64
@@ -384,6 +393,43 @@ class Codec:
         if self.m:
             self.rs_encode_shards(shards)
         return shards
+
+
+class Batcher:
+    """mec_batcher: concurrent PutObject calls of one geometry merged into shared launches.  encode() may be called from many
+    threads at once (ctypes releases the GIL for the duration of the call)."""
+
+    def __init__(self, k, m, block_size=1 << 20, device=0, max_batch_blocks=256, max_wait_us=200):
+        h = C.c_void_p()
+        rc = lib().mec_batcher_new(k, m, block_size, device, max_batch_blocks, max_wait_us, C.byref(h))
+        if rc:
+            raise MecError(rc, "mec_batcher_new")
+        self.h, self.k, self.m, self.n, self.block_size = h, k, m, k + m, block_size
+        self._sizes = Codec(k, m, block_size, device=device)
+
+    def encode(self, src, online=None, write_quorum=0, pinned=False):
+        """pinned=True: the part files are allocated page-locked (and `src` must be, e.g. a pinned_array) — the batch then moves
+        through the gather / scatter kernels instead of per-request copies.  The caller owns (and should free) those arrays."""
+        src = _u8(src)
+        fsz = self._sizes.bitrot_file_size(src.size)
+        online = [True] * self.n if online is None else online
+        mk = (lambda nb: pinned_array(max(nb, 1))[:nb]) if pinned else (lambda nb: np.zeros(nb, dtype=np.uint8))
+        files = [mk(fsz) if online[i] else None for i in range(self.n)]
+        rc = lib().mec_batcher_encode(self.h, src.ctypes.data if src.size else None, src.size, _ptrs(files), write_quorum)
+        if rc < 0:
+            raise MecError(rc, "mec_batcher_encode")
+        return files
+
+    def stat(self, name):
+        return lib().mec_batcher_stat(self.h, name.encode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().mec_batcher_free(self.h)
+            self.h = None
+            self._sizes.close()
+
+    __del__ = close
 
 
 def pinned_array(nbytes, device=None):

@@ -15,6 +15,7 @@
 #include "ec_engine.h"
 #include "whole_hash.cuh"
 #include "crc.cuh"
+#include "batch_copy.cuh"
 #include <nvtx3/nvToolsExt.h>
 
 struct NvtxRange {
@@ -37,7 +38,7 @@ static inline int64_t ceil_frac(int64_t num, int64_t den) {  // cmd/utils.go:689
 }
 static inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 6;
 
 // grow-only page-locked host staging (digests and digest verdicts: small, read by the host right after a stream drains)
 struct PinBuf {
@@ -61,7 +62,8 @@ struct PinBuf {
 struct Slot {
   DevBuf src, out, dig, aux, flags;  // aux: survivor arena of a reconstruct chunk / shard files of the whole-file path
   DevBuf crc_part, crc_out;          // object checksums of an encode chunk (crc.cuh)
-  PinBuf hdig, hflags, hcrc;
+  DevBuf dreq;                       // request table of a merged batch (batch_copy.cuh)
+  PinBuf hdig, hflags, hcrc, hreq;
   cudaStream_t st = nullptr;
 };
 
@@ -150,6 +152,7 @@ static int ensure_engine(mec_codec* c) {
         if (q.st) { cudaStreamDestroy(q.st); q.st = nullptr; }
       return MEC_ERR_CUDA;
     }
+
   c->eng = std::move(e);
   return MEC_OK;
 }
@@ -161,7 +164,7 @@ extern "C" void mec_codec_free(mec_codec* c) {
   for (auto& s : c->slots) {
     if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
     s.src.release(); s.out.release(); s.dig.release(); s.aux.release(); s.flags.release();
-    s.hdig.release(); s.hflags.release(); s.hcrc.release(); s.crc_part.release(); s.crc_out.release();
+    s.hdig.release(); s.hflags.release(); s.hcrc.release(); s.crc_part.release(); s.crc_out.release(); s.dreq.release(); s.hreq.release();
   }
   c->flags.release();
   c->crc_tables.release();
@@ -387,8 +390,14 @@ struct EncChunk {
   int64_t b0, nb;      // erasure blocks [b0, b0 + nb) of the call
   int64_t nfull;       // of which full (block_size) blocks; the call's short tail block, if in this chunk, follows them
   int64_t tail;        // bytes of that tail block (0 = none)
-  Slot* s;             // device buffers of this chunk: src (object bytes), out (parity at `pitch`), dig ([nb][n][32])
-  int64_t pitch;
+  Slot* s;             // slot whose stream carries the chunk
+  int64_t pitch;       // parity row pitch
+  // where the chunk lives: full blocks contiguous from d_src / d_out ((b*m + j)*pitch) / digests ([b][n][32]); the tail block
+  // has its own addresses (right behind the full blocks in the single-caller pipeline, elsewhere in a merged batch)
+  const uint8_t* d_src = nullptr; const uint8_t* d_src_tail = nullptr;
+  uint8_t* d_out = nullptr;       uint8_t* d_out_tail = nullptr;
+  const uint8_t* h_dig = nullptr; const uint8_t* h_dig_tail = nullptr;  // pinned host copies of the digests (frame sinks)
+  cudaStream_t st = nullptr;
 };
 
 // The 3-slot H2D -> fused kernel -> D2H pipeline behind every host-buffer encode entry point.  `enqueue(ch)` adds the
@@ -438,6 +447,11 @@ static int encode_pipeline(mec_codec* c, const uint8_t* src, int64_t len, Enqueu
     if ((rc = s.out.ensure(static_cast<size_t>(ch.nb * std::max(c->m, 1) * pitch)))) return rc;
     if ((rc = s.dig.ensure(static_cast<size_t>(ch.nb * c->n * 32)))) return rc;
     MEC_CUDA_OK(cudaMemcpyAsync(s.src.p, src + off, static_cast<size_t>(bytes), cudaMemcpyHostToDevice, s.st));
+    if ((rc = s.hdig.ensure(static_cast<size_t>(ch.nb * c->n * 32)))) return rc;
+    ch.st = s.st;
+    ch.d_src = static_cast<const uint8_t*>(s.src.p); ch.d_src_tail = ch.d_src + ch.nfull * bs;
+    ch.d_out = static_cast<uint8_t*>(s.out.p); ch.d_out_tail = ch.d_out + ch.nfull * c->m * pitch;
+    ch.h_dig = static_cast<const uint8_t*>(s.hdig.p); ch.h_dig_tail = ch.h_dig + ch.nfull * c->n * 32;
     if ((rc = encode_device_locked(c, static_cast<const uint8_t*>(s.src.p), bytes, static_cast<uint8_t*>(s.out.p), pitch,
                                    static_cast<uint8_t*>(s.dig.p), s.st)))
       return rc;
@@ -503,24 +517,21 @@ extern "C" int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, 
 //                   them); false leaves the data part to the caller (mec_encode_sg: the writer emits the digest followed
 //                   by the slice of its own source buffer, as streamingBitrotWriter.Write does — no copy anywhere)
 static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* files, bool with_data, uint8_t* data_digests) {
-  Slot& s = *ch.s;
-  const int k = c->k, m = c->m, n = c->n;
+  const int k = c->k, m = c->m;
   const int64_t bs = c->block_size, S = c->S(), fstride = 32 + S;
-  int rc;
-  if ((rc = s.hdig.ensure(static_cast<size_t>(ch.nb * n * 32)))) return rc;
-  MEC_CUDA_OK(cudaMemcpyAsync(s.hdig.p, s.dig.p, static_cast<size_t>(ch.nb * n * 32), cudaMemcpyDeviceToHost, s.st));
+  cudaStream_t st = ch.st;
   const int64_t per_t = ch.tail > 0 ? ceil_frac(ch.tail, k) : 0;
   for (int j = 0; j < m; j++) {
     uint8_t* f = files[k + j];
     if (!f) continue;
     f += ch.b0 * fstride + 32;
     if (ch.nfull > 0)
-      MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), static_cast<uint8_t*>(s.out.p) + j * ch.pitch,
+      MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), ch.d_out + j * ch.pitch,
                                     static_cast<size_t>(m * ch.pitch), static_cast<size_t>(S), static_cast<size_t>(ch.nfull),
-                                    cudaMemcpyDeviceToHost, s.st));
+                                    cudaMemcpyDeviceToHost, st));
     if (ch.tail > 0)
-      MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, static_cast<uint8_t*>(s.out.p) + (ch.nfull * m + j) * ch.pitch,
-                                  static_cast<size_t>(per_t), cudaMemcpyDeviceToHost, s.st));
+      MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, ch.d_out_tail + j * ch.pitch,
+                                  static_cast<size_t>(per_t), cudaMemcpyDeviceToHost, st));
     c->st_d2h += ch.nfull * S + per_t;
   }
   if (with_data) {
@@ -530,13 +541,13 @@ static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* file
       f += ch.b0 * fstride + 32;
       const int64_t w = std::max<int64_t>(0, std::min(S, bs - static_cast<int64_t>(i) * S));  // Split: the last shard is short, the rest is zero padding
       if (ch.nfull > 0 && w > 0)
-        MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), static_cast<const uint8_t*>(s.src.p) + static_cast<int64_t>(i) * S,
-                                      static_cast<size_t>(bs), static_cast<size_t>(w), static_cast<size_t>(ch.nfull), cudaMemcpyDeviceToHost, s.st));
+        MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), ch.d_src + static_cast<int64_t>(i) * S,
+                                      static_cast<size_t>(bs), static_cast<size_t>(w), static_cast<size_t>(ch.nfull), cudaMemcpyDeviceToHost, st));
       if (ch.tail > 0) {
         const int64_t start = static_cast<int64_t>(i) * per_t, have = std::max<int64_t>(0, std::min(per_t, ch.tail - start));
         if (have > 0)
-          MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, static_cast<const uint8_t*>(s.src.p) + ch.nfull * bs + start,
-                                      static_cast<size_t>(have), cudaMemcpyDeviceToHost, s.st));
+          MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, ch.d_src_tail + start,
+                                      static_cast<size_t>(have), cudaMemcpyDeviceToHost, st));
       }
       c->st_d2h += ch.nfull * w;
     }
@@ -548,12 +559,11 @@ static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* file
 static void frames_retire(mec_codec* c, const EncChunk& ch, uint8_t* const* files, bool with_data, uint8_t* data_digests) {
   const int k = c->k, n = c->n;
   const int64_t bs = c->block_size, S = c->S(), fstride = 32 + S;
-  const uint8_t* hd = static_cast<const uint8_t*>(ch.s->hdig.p);
   const int64_t per_t = ch.tail > 0 ? ceil_frac(ch.tail, k) : 0;
   for (int64_t b = 0; b < ch.nb; b++) {
     const bool is_tail = b >= ch.nfull;
     for (int i = 0; i < n; i++) {
-      const uint8_t* dg = hd + (b * n + i) * 32;
+      const uint8_t* dg = is_tail ? ch.h_dig_tail + i * 32 : ch.h_dig + (b * n + i) * 32;
       if (data_digests && i < k) memcpy(data_digests + ((ch.b0 + b) * k + i) * 32, dg, 32);
       uint8_t* f = files ? files[i] : nullptr;
       if (!f || (i < k && !with_data)) continue;
@@ -582,7 +592,11 @@ static int64_t encode_frames(mec_codec* c, const uint8_t* src, int64_t len, uint
   std::lock_guard<std::mutex> lk(c->mu);
   MEC_CUDA_OK(cudaSetDevice(c->device));
   rc = encode_pipeline(
-      c, src, len, [&](const EncChunk& ch) -> int { return frames_enqueue(c, ch, files, with_data, data_digests); },
+      c, src, len,
+      [&](const EncChunk& ch) -> int {
+        MEC_CUDA_OK(cudaMemcpyAsync(ch.s->hdig.p, ch.s->dig.p, static_cast<size_t>(ch.nb * c->n * 32), cudaMemcpyDeviceToHost, ch.st));
+        return frames_enqueue(c, ch, files, with_data, data_digests);
+      },
       [&](const EncChunk& ch) { frames_retire(c, ch, files, with_data, data_digests); });
   return rc ? rc : len;
 }
@@ -1707,4 +1721,323 @@ extern "C" int mec_selftest(int device) {
     }
   }
   return MEC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Cross-request coalescer.  MinIO builds one Erasure per request (cmd/erasure-object.go:1371) and encodes ONE block per loop
+// iteration (cmd/erasure-encode.go:76-108) on thousands of concurrent request goroutines (cmd/handler-api.go:139-143).  A GPU
+// launch that carries one 1 MiB block keeps one CTA busy on one of 148 SMs for as long as a launch of a thousand blocks takes.
+// The batcher turns concurrency into batch size: callers block in mec_batcher_encode*, a worker thread merges whatever is
+// queued (same k, m, block size by construction) into ONE staged buffer, ONE launch over all full blocks (plus one small
+// launch per short tail block), and one pass of DMA back into every caller's own frames; up to three merged batches are in
+// flight on the codec's three slots, so staging, kernel and copy-back of consecutive batches overlap.
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+
+struct BatchReq {
+  const uint8_t* src = nullptr;
+  int64_t len = 0;
+  uint8_t* const* files = nullptr;
+  uint8_t* data_digests = nullptr;
+  bool with_data = false;
+  bool mapped = false;   // every buffer of the call is page-locked (device-addressable): eligible for the gather / scatter kernels
+  int64_t result = 0;
+  bool done = false;
+  std::condition_variable cv;  // one per request: a finished batch wakes its own callers, not every thread parked in the batcher
+  EncChunk ch;   // placement inside the merged batch
+};
+
+struct mec_batcher {
+  mec_codec* codec = nullptr;
+  int64_t max_blocks = 256;
+  int max_wait_us = 200;
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done;
+  std::deque<BatchReq*> queue;
+  bool stop = false;
+  std::thread worker;
+  std::atomic<int64_t> st_batches{0}, st_requests{0}, st_blocks{0}, st_kernel_batches{0};
+};
+
+namespace {
+struct InflightBatch {
+  std::vector<BatchReq*> reqs;
+  bool busy = false;
+  bool needs_retire = true;  // false: the scatter kernel already assembled the frames
+};
+
+static void batcher_finish(mec_batcher* b, InflightBatch& fb, int rc) {
+  mec_codec* c = b->codec;
+  for (BatchReq* r : fb.reqs) {
+    if (rc == MEC_OK && fb.needs_retire) frames_retire(c, r->ch, r->files, r->with_data, r->data_digests);
+    r->result = rc == MEC_OK ? r->len : rc;
+  }
+  {
+    std::lock_guard<std::mutex> lk(b->mu);
+    for (BatchReq* r : fb.reqs) { r->done = true; r->cv.notify_one(); }  // under the lock: `r` lives on its caller's stack
+  }
+  fb.reqs.clear();
+  fb.busy = false;
+}
+
+// stage, launch and enqueue the copy-back of one merged batch on slot `s`
+static int batcher_submit(mec_batcher* b, Slot& s, std::vector<BatchReq*>& reqs, bool* needs_retire) {
+  mec_codec* c = b->codec;
+  const int k = c->k, m = c->m, n = c->n;
+  const int64_t bs = c->block_size, S = c->S(), pitch = round_up(S, 16);
+  *needs_retire = true;
+  bool all_mapped = n <= kBatchMaxFiles && getenv("MEC_BATCHER_MEMCPY") == nullptr;
+  for (BatchReq* r : reqs) all_mapped &= r->mapped;
+  int64_t total_full = 0, ntails = 0, tail_bytes = 0;
+  for (BatchReq* r : reqs) {
+    total_full += r->len / bs;
+    if (r->len % bs) { ntails++; tail_bytes += round_up(r->len % bs, 256); }
+  }
+  const int64_t nslots = total_full + ntails;
+  int rc;
+  if ((rc = s.src.ensure(static_cast<size_t>(total_full * bs + tail_bytes + 512)))) return rc;
+  if ((rc = s.out.ensure(static_cast<size_t>(std::max<int64_t>(nslots, 1) * std::max(m, 1) * pitch)))) return rc;
+  if ((rc = s.dig.ensure(static_cast<size_t>(std::max<int64_t>(nslots, 1) * n * 32)))) return rc;
+  if ((rc = s.hdig.ensure(static_cast<size_t>(std::max<int64_t>(nslots, 1) * n * 32)))) return rc;
+  uint8_t* dsrc = static_cast<uint8_t*>(s.src.p);
+  uint8_t* dout = static_cast<uint8_t*>(s.out.p);
+  uint8_t* ddig = static_cast<uint8_t*>(s.dig.p);
+  const uint8_t* hdig = static_cast<const uint8_t*>(s.hdig.p);
+  int64_t fb = 0, tb = total_full, toff = total_full * bs;
+  if (all_mapped) {
+    // gather kernel -> ONE fused launch over all full blocks (+ one per tail) -> scatter kernel: a handful of launches and one
+    // small table copy per batch, whatever the number of requests
+    if ((rc = s.hreq.ensure(reqs.size() * sizeof(BatchReqDesc)))) return rc;
+    if ((rc = s.dreq.ensure(reqs.size() * sizeof(BatchReqDesc)))) return rc;
+    BatchReqDesc* tab = static_cast<BatchReqDesc*>(s.hreq.p);
+    int64_t max_len = 0, max_nb = 0;
+    for (size_t q = 0; q < reqs.size(); q++) {
+      BatchReq* r = reqs[q];
+      BatchReqDesc& d = tab[q];
+      memset(&d, 0, sizeof(d));
+      const int64_t nf = r->len / bs, tl = r->len % bs;
+      d.src = r->src; d.len = r->len; d.data_digests = r->data_digests; d.with_data = r->with_data ? 1 : 0;
+      for (int i = 0; i < n; i++) d.files[i] = r->files[i];
+      d.full0 = fb; d.tail_slot = tl ? tb : -1; d.tail_src_off = tl ? toff : 0;
+      r->ch = EncChunk();
+      r->ch.nfull = nf; r->ch.tail = tl;
+      r->ch.d_src_tail = dsrc + toff; r->ch.d_out_tail = dout + tb * m * pitch; r->ch.h_dig_tail = hdig + tb * n * 32;
+      fb += nf;
+      if (tl) { tb++; toff += round_up(tl, 256); }
+      max_len = std::max(max_len, r->len);
+      max_nb = std::max(max_nb, nf + (tl ? 1 : 0));
+      c->st_h2d += r->len;
+      c->st_d2h += (nf * S + (tl ? ceil_frac(tl, k) : 0)) * (r->with_data ? n : m);
+    }
+    MEC_CUDA_OK(cudaMemcpyAsync(s.dreq.p, tab, reqs.size() * sizeof(BatchReqDesc), cudaMemcpyHostToDevice, s.st));
+    BatchCopyParams cp;
+    cp.reqs = static_cast<const BatchReqDesc*>(s.dreq.p);
+    cp.nreq = static_cast<int>(reqs.size()); cp.k = k; cp.m = m; cp.bs = bs; cp.S = S; cp.pitch = pitch;
+    cp.staged = dsrc; cp.parity = dout; cp.digests = ddig;
+    // staging: the copy engines are the faster reader of host memory (one call per request); the gather kernel (SM loads over
+    // PCIe, no per-request call at all) is kept for hosts where the worker thread is the bottleneck — measured in profiles/r2_concurrency.md
+    static const bool use_gather = getenv("MEC_BATCHER_GATHER") != nullptr;
+    if (use_gather) {
+      const unsigned gx = static_cast<unsigned>(std::min<int64_t>(64, std::max<int64_t>(1, ceil_frac(max_len, 32 << 10))));
+      batch_gather_kernel<<<dim3(gx, static_cast<unsigned>(reqs.size())), 256, 0, s.st>>>(cp);
+      MEC_CUDA_OK(cudaGetLastError());
+      c->eng->count_launch();
+    } else {
+      for (size_t q = 0; q < reqs.size(); q++) {
+        const BatchReqDesc& d = tab[q];
+        const int64_t fbytes = d.len / bs * bs, tl = d.len - fbytes;
+        cudaStream_t cs = s.st;  // (spreading the copies over a second stream / copy engine was measured: no gain)
+        if (fbytes > 0) MEC_CUDA_OK(cudaMemcpyAsync(dsrc + d.full0 * bs, d.src, static_cast<size_t>(fbytes), cudaMemcpyHostToDevice, cs));
+        if (tl > 0) MEC_CUDA_OK(cudaMemcpyAsync(dsrc + d.tail_src_off, d.src + fbytes, static_cast<size_t>(tl), cudaMemcpyHostToDevice, cs));
+      }
+
+    }
+    if (total_full > 0 && (rc = encode_device_locked(c, dsrc, total_full * bs, dout, pitch, ddig, s.st))) return rc;
+    for (BatchReq* r : reqs)
+      if (r->ch.tail > 0 && (rc = encode_device_locked(c, r->ch.d_src_tail, r->ch.tail, r->ch.d_out_tail, pitch, ddig + (r->ch.h_dig_tail - hdig), s.st)))
+        return rc;
+    batch_scatter_kernel<<<dim3(static_cast<unsigned>(std::min<int64_t>(max_nb, 16)), static_cast<unsigned>(n), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(cp);
+    MEC_CUDA_OK(cudaGetLastError());
+    c->eng->count_launch();
+    *needs_retire = false;
+    c->st_blocks_encoded += nslots;
+    b->st_batches++;
+    b->st_kernel_batches++;
+    b->st_requests += static_cast<int64_t>(reqs.size());
+    b->st_blocks += nslots;
+    return MEC_OK;
+  }
+  for (BatchReq* r : reqs) {
+    EncChunk& ch = r->ch;
+    ch = EncChunk();
+    ch.b0 = 0; ch.nfull = r->len / bs; ch.tail = r->len % bs; ch.nb = ch.nfull + (ch.tail ? 1 : 0);
+    ch.s = &s; ch.st = s.st; ch.pitch = pitch;
+    ch.d_src = dsrc + fb * bs; ch.d_out = dout + fb * m * pitch; ch.h_dig = hdig + fb * n * 32;
+    if (ch.nfull > 0)
+      MEC_CUDA_OK(cudaMemcpyAsync(dsrc + fb * bs, r->src, static_cast<size_t>(ch.nfull * bs), cudaMemcpyHostToDevice, s.st));
+    if (ch.tail > 0) {
+      ch.d_src_tail = dsrc + toff; ch.d_out_tail = dout + tb * m * pitch; ch.h_dig_tail = hdig + tb * n * 32;
+      MEC_CUDA_OK(cudaMemcpyAsync(dsrc + toff, r->src + ch.nfull * bs, static_cast<size_t>(ch.tail), cudaMemcpyHostToDevice, s.st));
+      toff += round_up(ch.tail, 256);
+      tb++;
+    }
+    fb += ch.nfull;
+    c->st_h2d += r->len;
+  }
+  if (total_full > 0 && (rc = encode_device_locked(c, dsrc, total_full * bs, dout, pitch, ddig, s.st))) return rc;  // ONE launch for every caller's full blocks
+  for (BatchReq* r : reqs) {
+    const EncChunk& ch = r->ch;
+    if (ch.tail > 0 && (rc = encode_device_locked(c, ch.d_src_tail, ch.tail, ch.d_out_tail, pitch,
+                                                  ddig + (ch.h_dig_tail - hdig), s.st)))
+      return rc;
+  }
+  MEC_CUDA_OK(cudaMemcpyAsync(s.hdig.p, s.dig.p, static_cast<size_t>(nslots * n * 32), cudaMemcpyDeviceToHost, s.st));
+  for (BatchReq* r : reqs)
+    if ((rc = frames_enqueue(c, r->ch, r->files, r->with_data, r->data_digests))) return rc;
+  c->st_blocks_encoded += nslots;
+  b->st_batches++;
+  b->st_requests += static_cast<int64_t>(reqs.size());
+  b->st_blocks += nslots;
+  (void)k;
+  return MEC_OK;
+}
+
+static void batcher_main(mec_batcher* b) {
+  mec_codec* c = b->codec;
+  cudaSetDevice(c->device);
+  InflightBatch inflight[kSlots];
+  int head = 0, tail = 0, nbusy = 0;
+  for (;;) {
+    std::vector<BatchReq*> reqs;
+    {
+      std::unique_lock<std::mutex> lk(b->mu);
+      if (nbusy == 0) b->cv_work.wait(lk, [&] { return b->stop || !b->queue.empty(); });
+      if (b->stop && b->queue.empty() && nbusy == 0) return;
+      if (!b->queue.empty() && nbusy < kSlots) {
+        // gather: whatever is queued now; when nothing is in flight, give concurrent callers max_wait_us to join
+        auto blocks_queued = [&] {
+          int64_t nb = 0;
+          for (BatchReq* r : b->queue) nb += ceil_frac(r->len, c->block_size);
+          return nb;
+        };
+        // an idle GPU gives the first caller up to max_wait_us of company before its batch is cut
+        // (measured, profiles/r2_concurrency.md: waiting while batches are in flight only adds latency to a closed loop of callers)
+        if (nbusy == 0 && b->max_wait_us > 0 && blocks_queued() < b->max_blocks)
+          b->cv_work.wait_for(lk, std::chrono::microseconds(b->max_wait_us), [&] { return b->stop || blocks_queued() >= b->max_blocks; });
+        int64_t nb = 0;
+        while (!b->queue.empty()) {
+          BatchReq* r = b->queue.front();
+          const int64_t rb = ceil_frac(r->len, c->block_size);
+          if (!reqs.empty() && nb + rb > b->max_blocks) break;
+          reqs.push_back(r);
+          b->queue.pop_front();
+          nb += rb;
+        }
+      }
+    }
+    if (!reqs.empty()) {
+      Slot& s = c->slots[head];
+      int rc;
+      {
+        std::lock_guard<std::mutex> lk(c->mu);
+        rc = batcher_submit(b, s, reqs, &inflight[head].needs_retire);
+      }
+      inflight[head].reqs = reqs;
+      inflight[head].busy = true;
+      if (rc != MEC_OK) {  // drain what was enqueued before the failure, then fail the whole batch
+        cudaStreamSynchronize(s.st);
+        batcher_finish(b, inflight[head], rc);
+      } else {
+        head = (head + 1) % kSlots;
+        nbusy++;
+      }
+      bool more;
+      {
+        std::lock_guard<std::mutex> lk(b->mu);
+        more = !b->queue.empty();
+      }
+      if (more && nbusy < kSlots) continue;  // keep the slots full before waiting on the oldest batch
+    }
+    if (nbusy > 0) {
+      const cudaError_t e = cudaStreamSynchronize(c->slots[tail].st);
+      batcher_finish(b, inflight[tail], e == cudaSuccess ? MEC_OK : MEC_ERR_CUDA);
+      tail = (tail + 1) % kSlots;
+      nbusy--;
+    }
+  }
+}
+}  // namespace
+
+extern "C" int mec_batcher_new(int k, int m, int64_t block_size, int device, int64_t max_batch_blocks, int max_wait_us, mec_batcher** out) {
+  if (!out) return MEC_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  mec_codec* c = nullptr;
+  int rc = mec_codec_new(k, m, block_size, MEC_HIGHWAYHASH256S, device, &c);
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(c->mu);
+    rc = ensure_engine(c);
+  }
+  if (rc) { mec_codec_free(c); return rc; }
+  if (c->S() >= (1ll << 31)) { mec_codec_free(c); return MEC_ERR_UNSUPPORTED; }
+  mec_batcher* b = new mec_batcher;
+  b->codec = c;
+  if (max_batch_blocks > 0) b->max_blocks = max_batch_blocks;
+  if (max_wait_us >= 0) b->max_wait_us = max_wait_us;
+  b->worker = std::thread(batcher_main, b);
+  *out = b;
+  return MEC_OK;
+}
+
+extern "C" void mec_batcher_free(mec_batcher* b) {
+  if (!b) return;
+  {
+    std::lock_guard<std::mutex> lk(b->mu);
+    b->stop = true;
+  }
+  b->cv_work.notify_all();
+  if (b->worker.joinable()) b->worker.join();
+  mec_codec_free(b->codec);
+  delete b;
+}
+
+static int64_t batcher_call(mec_batcher* b, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* data_digests, bool with_data,
+                            int write_quorum) {
+  if (!b || len < 0 || !files || (len > 0 && !src)) return MEC_ERR_INVALID_ARGUMENT;
+  int online = 0;
+  for (int i = 0; i < b->codec->n; i++) online += files[i] != nullptr;
+  if (online < write_quorum) return MEC_ERR_WRITE_QUORUM;  // cmd/erasure-encode.go:59-65
+  if (len == 0) return 0;
+  BatchReq r;
+  r.src = src; r.len = len; r.files = files; r.data_digests = data_digests; r.with_data = with_data;
+  // page-locked buffers (mec_alloc_pinned*, or anything cudaHostRegister'ed) are moved by the gather / scatter kernels; checked here,
+  // on the caller's thread, so the worker does not pay for it
+  r.mapped = mec_is_pinned(src) && (!data_digests || mec_is_pinned(data_digests));
+  for (int i = 0; i < b->codec->n && r.mapped; i++)
+    if (files[i] && (i >= b->codec->k || with_data)) r.mapped = mec_is_pinned(files[i]) != 0;
+  std::unique_lock<std::mutex> lk(b->mu);
+  if (b->stop) return MEC_ERR_INVALID_ARGUMENT;
+  b->queue.push_back(&r);
+  if (b->queue.size() == 1 || static_cast<int64_t>(b->queue.size()) * std::max<int64_t>(1, len / b->codec->block_size) >= b->max_blocks)
+    b->cv_work.notify_one();  // the worker is woken by the first arrival and by the one that fills the batch, not by every caller
+  r.cv.wait(lk, [&] { return r.done; });
+  return r.result;
+}
+extern "C" int64_t mec_batcher_encode(mec_batcher* b, const uint8_t* src, int64_t len, uint8_t* const* files, int write_quorum) {
+  return batcher_call(b, src, len, files, nullptr, true, write_quorum);
+}
+extern "C" int64_t mec_batcher_encode_sg(mec_batcher* b, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* data_digests,
+                                         int write_quorum) {
+  if (!data_digests) return MEC_ERR_INVALID_ARGUMENT;
+  return batcher_call(b, src, len, files, data_digests, false, write_quorum);
+}
+extern "C" int64_t mec_batcher_stat(const mec_batcher* b, const char* name) {
+  if (!b || !name) return -1;
+  if (!strcmp(name, "batches")) return b->st_batches.load();
+  if (!strcmp(name, "requests")) return b->st_requests.load();
+  if (!strcmp(name, "blocks")) return b->st_blocks.load();
+  if (!strcmp(name, "kernel_batches")) return b->st_kernel_batches.load();
+  if (!strcmp(name, "launches")) return b->codec->eng ? b->codec->eng->launches() : 0;
+  return -1;
 }

@@ -179,6 +179,15 @@ extern "C" void mec_free_pinned(void* p) {
 
 // 1 when [p, p + bytes) is page-locked memory known to CUDA (DMA engines copy straight from / into it)
 extern "C" int mec_is_pinned(const void* p) {
+  {  // buffers from mec_alloc_pinned* are answered from the registry: no driver call (and no driver lock) on the request path
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto& reg = registry();
+    auto it = reg.upper_bound(const_cast<void*>(p));
+    if (it != reg.begin()) {
+      --it;
+      if (static_cast<const char*>(p) < static_cast<const char*>(it->first) + it->second.bytes) return 1;
+    }
+  }
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return 0; }
   return at.type == cudaMemoryTypeHost ? 1 : 0;

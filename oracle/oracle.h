@@ -146,6 +146,7 @@ uint64_t orc_crc32(const uint8_t *p, size_t n);
 uint64_t orc_crc32c(const uint8_t *p, size_t n);
 uint64_t orc_crc64nvme(const uint8_t *p, size_t n);
 
+void orc_encode_hash_blocks_st(int k, int m, int64_t block_size, const uint8_t *src, int64_t nblocks, uint8_t *parity, uint8_t *digests);
 typedef struct orc_pool orc_pool;
 orc_pool *orc_pool_new(int threads);
 void orc_pool_fill(orc_pool *p, int k, int m, int64_t block_size, uint8_t *src, int64_t nblocks, uint8_t *parity, uint8_t *digests, uint64_t seed);

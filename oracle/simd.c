@@ -193,6 +193,24 @@ static void *mt_worker(void *vp) {
   return NULL;
 }
 
+/* single-threaded, on the calling thread (the per-request shape: every MinIO request goroutine encodes its own blocks) */
+void orc_encode_hash_blocks_st(int k, int m, int64_t bs, const uint8_t *src, int64_t nblocks, uint8_t *parity, uint8_t *digests) {
+  static uint8_t *mat = NULL;
+  static int mk = 0, mm = 0;
+  static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+  pthread_mutex_lock(&mu);
+  if (!mat || mk != k || mm != m) {
+    uint8_t *nm = (uint8_t *)malloc((size_t)(k + m) * k);
+    orc_rs_matrix(k, m, nm);
+    orc_gf_mul(1, 1);
+    mat = nm; mk = k; mm = m; /* the previous matrix (if any) is leaked on purpose: other threads may still read it */
+  }
+  const uint8_t *rows = mat + (size_t)k * k;
+  pthread_mutex_unlock(&mu);
+  mt_arg a = {k, m, 0, 1, 1, bs, nblocks, src, parity, digests, rows};
+  mt_worker(&a);
+}
+
 double orc_encode_hash_blocks_mt(int k, int m, int64_t bs, const uint8_t *src, int64_t nblocks,
                                  uint8_t *parity, uint8_t *digests, int threads, int reps) {
   if (threads < 1) threads = 1;

@@ -307,3 +307,51 @@ def test_whole_file_decode_and_heal_with_bitrot(mb, oracle, algo):
         c.decode_whole([None if i in (0, 3) else bad[i] for i in range(n)], sums, 0, size, size)
     assert ei.value.code == -10
     c.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_batcher_merges_concurrent_puts(mb, oracle, pinned):
+    """Many threads PUT objects of different sizes through one mec_batcher: every caller gets exactly the frames a private
+    mec_encode would have produced, and the calls were merged into far fewer launches than there were requests.
+    pinned: page-locked buffers -> the gather / scatter kernels move the batch; pageable -> per-request copies."""
+    import threading
+    k, m, bs = 12, 4, MiB
+    sizes = [MiB, 2 * MiB, MiB + 4321, 3 * MiB + 7, 100, MiB - 1, 5 * MiB, MiB, 33, 2 * MiB + 1]
+    nthreads, rounds = 32, 6
+    bat = mb.Batcher(k, m, bs, max_batch_blocks=128, max_wait_us=2000)
+    datas = [rand(sizes[t % len(sizes)], 900 + t) for t in range(nthreads)]
+    if pinned:
+        pd = []
+        for d in datas:
+            a = mb.pinned_array(d.size)[:d.size]
+            a[:] = d
+            pd.append(a)
+        datas = pd
+    want = [oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, d)[0] for d in datas]
+    errs = []
+
+    def worker(t):
+        try:
+            for _ in range(rounds):
+                files = bat.encode(datas[t], pinned=pinned)
+                for i in range(k + m):
+                    if not np.array_equal(files[i], want[t][i]):
+                        errs.append((t, i))
+                if pinned:
+                    for f in files:
+                        mb.lib().mec_free_pinned(f.ctypes.data)
+        except Exception as e:  # noqa: BLE001
+            errs.append((t, repr(e)))
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs[:5]
+    assert bat.stat("requests") == nthreads * rounds
+    assert bat.stat("batches") < bat.stat("requests")        # callers were coalesced
+    assert (bat.stat("kernel_batches") > 0) == pinned
+    # quorum and empty objects behave like mec_encode
+    with pytest.raises(mb.MecError) as ei:
+        bat.encode(rand(1000, 1), online=[True] * 12 + [False] * 4, write_quorum=13)
+    assert ei.value.code == -11
+    assert all(f.size == 0 for f in bat.encode(b""))
+    bat.close()
