@@ -421,6 +421,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   // ---- erasure blocks per CTA and block size
   int eb = opt.eb > 0 ? opt.eb : (128 / (2 * n) > 0 ? 128 / (2 * n) : 1);
   if (opt.eb <= 0 && d.static_encode && d.contiguous) eb = kStaticEb;  // OOB blocks of a partial group read as zeros
+  if (opt.eb <= 0 && !d.contiguous && d.r > 0 && 2 * n * kStaticEb <= 256) eb = kStaticEb;  // reconstruct: the compile-time CTA shape (NVRTC kernels are EB_T = 4)
   if (opt.eb <= 0)  // small launches: shrink the CTA until there are at least ~2 CTAs per SM
     while (eb > 1 && (d.nblocks + eb - 1) / eb < 2ll * num_sms_) eb >>= 1;
   if (false) {}
@@ -518,11 +519,51 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     }
     direct = use_tma && !any_misaligned;  // runtime-matrix and NVRTC kernels for aligned rows are ALIGN == 0 instantiations
     if (use_tma) {
-      p.tma_mode = kLoadTmaPerInput;
-      for (int t = 0; t < d.k; t++) {
-        int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], static_cast<uint64_t>(row_bytes / 4), static_cast<uint64_t>(d.nblocks),
-                          static_cast<uint64_t>(row_bytes), (direct ? kRowPitch : kRawRow) / 4, static_cast<uint32_t>(eb));
-        if (rc) return rc;
+      // runs of rows at a uniform stride with the same offset inside their block row: one 3-D map (and one request per tile) per run
+      int nruns = 0, run0[kMaxRuns + 1] = {0};
+      int64_t run_stride[kMaxRuns] = {0};
+      // a 3-D box lays its rows out back to back (eb x row bytes each): that must be the kernel's row-group pitch
+      const uint32_t rowb = direct ? kRowPitch : kRawRow;
+      bool runs_ok = !opt.no_rows3d && raw_group_bytes(eb, static_cast<int>(rowb)) == static_cast<uint32_t>(eb) * rowb;
+      for (int t = 0; t < d.k && runs_ok;) {
+        if (nruns == kMaxRuns) { runs_ok = false; break; }
+        int len = 1;
+        int64_t stride = 0;
+        while (t + len < d.k) {
+          const int64_t st = d.map_base[t + len] - d.map_base[t + len - 1];
+          if (len == 1) {
+            if (st <= 0 || (st & 15) || st < row_bytes * (d.nblocks > 1 ? d.nblocks : 1)) break;
+            stride = st;
+          } else if (st != stride) {
+            break;
+          }
+          if (p.in_c0[t + len] != p.in_c0[t] || p.in_align[t + len] != p.in_align[t]) break;
+          len++;
+        }
+        run0[nruns] = t;
+        run_stride[nruns] = stride;
+        nruns++;
+        t += len;
+      }
+      if (runs_ok && nruns < d.k) {  // at least one run is longer than a row: worth it
+        run0[nruns] = d.k;
+        p.tma_mode = kLoadTmaRuns;
+        p.nruns = nruns;
+        for (int q = 0; q <= nruns; q++) p.run_row0[q] = static_cast<uint8_t>(run0[q]);
+        for (int q = 0; q < nruns; q++) {
+          const int len = run0[q + 1] - run0[q];
+          int rc = make_map(encode_tiled_, &maps.m[q], d.map_base[run0[q]], static_cast<uint64_t>(row_bytes / 4), static_cast<uint64_t>(d.nblocks),
+                            static_cast<uint64_t>(row_bytes), (direct ? kRowPitch : kRawRow) / 4, static_cast<uint32_t>(eb), static_cast<uint64_t>(len),
+                            static_cast<uint64_t>(len > 1 ? run_stride[q] : row_bytes), static_cast<uint32_t>(len));
+          if (rc) return rc;
+        }
+      } else {
+        p.tma_mode = kLoadTmaPerInput;
+        for (int t = 0; t < d.k; t++) {
+          int rc = make_map(encode_tiled_, &maps.m[t], d.map_base[t], static_cast<uint64_t>(row_bytes / 4), static_cast<uint64_t>(d.nblocks),
+                            static_cast<uint64_t>(row_bytes), (direct ? kRowPitch : kRawRow) / 4, static_cast<uint32_t>(eb));
+          if (rc) return rc;
+        }
       }
     }
   }

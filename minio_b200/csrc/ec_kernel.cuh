@@ -38,7 +38,8 @@ constexpr int kMaxMaps = 16;     // tensor maps carried in kernel params
 constexpr int kRChunk = 4;       // widest row chunk of the runtime-matrix GF step (mask table padding)
 constexpr int kAlignRuntime = -1;
 
-enum LoaderMode : int { kLoadBytewise = 0, kLoadTmaBlocks2D = 1, kLoadTmaPerInput = 2 };
+enum LoaderMode : int { kLoadBytewise = 0, kLoadTmaBlocks2D = 1, kLoadTmaPerInput = 2, kLoadTmaRuns = 3 };
+constexpr int kMaxRuns = 6;      // runs of uniformly spaced input rows fetched with one 3-D request each (kLoadTmaRuns)
 
 struct alignas(64) TmaMaps {
   CUtensorMap m[kMaxMaps];
@@ -65,6 +66,8 @@ struct FusedParams {
   uint8_t* corrupt;                // optional [nblocks][k], set to 1 on digest mismatch
   uint64_t key[4];                 // HighwayHash key (cmd/bitrot.go:37 for bitrot)
   uint8_t coef[kMaxR][kMaxK];      // runtime matrix (GfDynamic only)
+  int32_t nruns;                   // kLoadTmaRuns: input rows [run_row0[q], run_row0[q+1]) share tensor map q (x, block, row)
+  uint8_t run_row0[kMaxRuns + 1];
   uint32_t* work_counter;          // optional: groups beyond the first of every CTA are claimed from this counter (zeroed per launch)
 };
 
@@ -322,6 +325,15 @@ __global__ void __launch_bounds__((fused_max_threads<GF, EB_T>()), (fused_min_bl
           for (int t = part; t < k; t += parts)
             tma_load_2d(dst0 + static_cast<uint32_t>(t) * group_bytes, &maps.m[0], (p.in_c0[t] + i * kTile) >> 2,
                         static_cast<int32_t>(b0), bar);
+        } else if (p.tma_mode == kLoadTmaRuns) {
+          // survivors that sit at a uniform stride (one staging arena, or shard files of one allocation) arrive with ONE 3-D
+          // request per run — (x, erasure block, row) — instead of one 2-D request per row from every warp
+          if (part == 0) {
+            mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * rawp);
+            for (int q = 0; q < p.nruns; q++)
+              tma_load_3d(dst0 + static_cast<uint32_t>(p.run_row0[q]) * group_bytes, &maps.m[q], (p.in_c0[p.run_row0[q]] + i * kTile) >> 2,
+                          static_cast<int32_t>(b0), 0, bar);
+          }
         } else {  // one map per input stream: rows = erasure blocks of that stream, box {272 B, eb blocks}
           if (part == 0) mbar_expect_tx(bar, static_cast<uint32_t>(k) * eb * rawp);
           for (int t = part; t < k; t += parts)

@@ -66,8 +66,9 @@ def frames_from(k, m, bs, nblocks, src, par, dig, S):
     frames = []
     src2 = src.view(nblocks, bs)
     par3 = par.view(nblocks, m, -1)
+    arena = torch.zeros((k + m, nblocks, fp), dtype=torch.uint8, device=dev)  # one allocation: shard files at a uniform stride (run-wise 3-D TMA fetch)
     for i in range(k + m):
-        f = torch.zeros((nblocks, fp), dtype=torch.uint8, device=dev)
+        f = arena[i]
         f[:, :32] = dig[:, i]
         if i < k:
             lo, hi = i * S, min((i + 1) * S, bs)
@@ -265,6 +266,12 @@ if __name__ == "__main__":
         for _ in range(3):
             jit_encode_case(10, 4, MiB, 4096)
         jit_encode_case(10, 4, MiB, 8192)
+        sys.exit(0)
+    if only == "4k":   # one case, e.g. under ncu
+        reconstruct_case("4: RS(16,4) heal shape, stale {0,7,16,19}", 16, 4, MiB, int(sys.argv[2]) if len(sys.argv) > 2 else 2960, {0, 7, 16, 19}, 4, 0)
+        sys.exit(0)
+    if only == "3b":
+        reconstruct_case("3b: RS(12,4) heal shape, shards {1,5,12,15} stale", 12, 4, MiB, int(sys.argv[2]) if len(sys.argv) > 2 else 3552, {1, 5, 12, 15}, 3, 0)
         sys.exit(0)
     if only == "3a":   # one case, e.g. under ncu
         reconstruct_case("3a: RS(12,4) GetObject shape, data shards {0,1,2,3} erased", 12, 4, MiB, int(sys.argv[2]) if len(sys.argv) > 2 else 3552, {0, 1, 2, 3}, 3, 3)
