@@ -256,10 +256,12 @@ int mec_selftest(int device);
  * "jit": run-time specialisation of decode matrices / uncompiled (k, m) geometries with NVRTC, cached per process:
  *   -1 (default) a pattern that has been seen with 32 MiB of input is compiled on a background thread; calls that
  *      arrive before it is ready run the generic runtime-matrix kernel — no request ever waits for the compiler;
- *    1 compile (or wait for the background compile) inside the call — tests and benchmarks;  0 never specialise. */
+ *    1 compile (or wait for the background compile) inside the call — tests and benchmarks;  0 never specialise.
+ * Compiled kernels are also kept on disk (MEC_JIT_CACHE_DIR, default $HOME/.cache/minio_b200, "off" disables), keyed by the kernel
+ * sources, options and matrix: a restarted process loads the kernel of a pattern it has met before instead of recompiling. */
 int mec_set_option(mec_codec* c, const char* name, int64_t value);
 /* Boundary counters (SURVEY §5 metrics row): name is one of "launches", "blocks_encoded", "blocks_read",
- * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms" (both process-wide), "jit_launches".  -1 for unknown names.
+ * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms", "jit_disk_hits" (process-wide), "jit_launches".  -1 for unknown names.
  * Every ABI call is also wrapped in an NVTX range (visible in Nsight Systems) — the tracing hook of SURVEY §5. */
 int64_t mec_get_stat(const mec_codec* c, const char* name);
 /* Stops background kernel specialisation and waits for a compile in flight.  Call before the process exits (exit()

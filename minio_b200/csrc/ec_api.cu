@@ -200,6 +200,7 @@ extern "C" int64_t mec_get_stat(const mec_codec* c, const char* name) {
   if (!strcmp(name, "jit_compiles")) return c->eng ? c->eng->jit_compiles() : 0;
   if (!strcmp(name, "jit_launches")) return c->eng ? c->eng->jit_launches() : 0;
   if (!strcmp(name, "jit_ms")) return c->eng ? static_cast<int64_t>(c->eng->jit_seconds() * 1e3) : 0;
+  if (!strcmp(name, "jit_disk_hits")) return c->eng ? c->eng->jit_disk_hits() : 0;
   return -1;
 }
 extern "C" void mec_shutdown(void) { mec::jit_shutdown(); }

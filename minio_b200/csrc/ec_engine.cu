@@ -3,6 +3,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <atomic>
 #include <nvrtc.h>
 #include <chrono>
 #include <condition_variable>
@@ -174,8 +177,61 @@ void jit_quiesce() {
   g.cv_done.wait(lk, [&] { return !g.worker_busy; });
 }
 
+// On-disk cache of specialised kernels (option: MEC_JIT_CACHE_DIR, default $HOME/.cache/minio_b200; "off" disables): a cubin per
+// (kernel sources, compile options, instantiation, matrix), so that a restarted server — or the next process of a heal sweep —
+// loads the kernel of an erasure pattern it has met before in a millisecond instead of recompiling for half a second.  Entries
+// are keyed by a 64-bit FNV-1a of everything that goes into the compile; files are written to a temporary name and renamed.
+static uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+  const unsigned char* p = static_cast<const unsigned char*>(data);
+  for (size_t i = 0; i < n; i++) { h ^= p[i]; h *= 1099511628211ull; }
+  return h;
+}
+static std::string jit_cache_dir() {
+  const char* e = getenv("MEC_JIT_CACHE_DIR");
+  if (e && !strcmp(e, "off")) return "";
+  std::string d;
+  if (e && *e) d = e;
+  else if (const char* h = getenv("HOME")) d = std::string(h) + "/.cache/minio_b200";
+  else return "";
+  std::string cur;
+  for (size_t i = 0; i <= d.size(); i++) {  // mkdir -p
+    if (i == d.size() || d[i] == '/') {
+      if (!cur.empty()) mkdir(cur.c_str(), 0700);
+    }
+    if (i < d.size()) cur += d[i];
+  }
+  return d;
+}
+static bool read_file(const std::string& path, std::vector<char>* out) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) return false;
+  fseek(f, 0, SEEK_END);
+  const long n = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  bool ok = n > 0;
+  if (ok) {
+    out->resize(static_cast<size_t>(n));
+    ok = fread(out->data(), 1, static_cast<size_t>(n), f) == static_cast<size_t>(n);
+  }
+  fclose(f);
+  return ok;
+}
+static void write_file_atomic(const std::string& path, const void* data, size_t n) {
+  const std::string tmp = path + ".tmp" + std::to_string(static_cast<long long>(getpid()));
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return;
+  const bool ok = fwrite(data, 1, n, f) == n;
+  fclose(f);
+  if (ok) rename(tmp.c_str(), path.c_str());
+  else remove(tmp.c_str());
+}
+
 // NVRTC-instantiate the kernel template for one concrete matrix; returns a cudaKernel_t or nullptr
 // load == false stops after NVRTC (no device needed): the CPU-side check that the embedded headers still specialise
+static std::atomic<int64_t>& jit_cache_hits() {
+  static std::atomic<int64_t> n{0};
+  return n;
+}
 void* compile_specialised(const JitSpec& sp, bool load = true) {
   NvrtcApi& api = nvrtc_api();
   if (!api.ok) return nullptr;
@@ -203,6 +259,39 @@ void* compile_specialised(const JitSpec& sp, bool load = true) {
                         "-DMEC_HH_MUL=" MEC_STR(MEC_HH_MUL), "-DMEC_HH_VARIANT=" MEC_STR(MEC_HH_VARIANT),
                         "-DMEC_MIN_BLOCKS=" MEC_STR(MEC_MIN_BLOCKS),
                         "-DMEC_GF_LEVEL=" MEC_STR(MEC_GF_LEVEL), "-DMEC_GF_GROUP=" MEC_STR(MEC_GF_GROUP)};
+  // disk cache: the key covers the embedded headers, the generated source, the instantiation and the options
+  std::string cache_path, cached_name;
+  if (load) {
+    const std::string dir = jit_cache_dir();
+    if (!dir.empty()) {
+      uint64_t h = 14695981039346656037ull;
+      for (const char* b : bodies) h = fnv1a(h, b, strlen(b));
+      h = fnv1a(h, src.data(), src.size());
+      h = fnv1a(h, expr_s.data(), expr_s.size());
+      for (const char* o : opts) h = fnv1a(h, o, strlen(o));
+      char name[64];
+      snprintf(name, sizeof(name), "/k%016llx.cubin", static_cast<unsigned long long>(h));
+      cache_path = dir + name;
+      std::vector<char> blob;
+      // file = [u32 length of the lowered kernel name][name][cubin]
+      if (read_file(cache_path, &blob) && blob.size() > 8) {
+        uint32_t nl = 0;
+        memcpy(&nl, blob.data(), 4);
+        if (nl > 0 && nl < 4096 && blob.size() > 4 + nl) {
+          cached_name.assign(blob.data() + 4, nl);
+          cudaLibrary_t lib = nullptr;
+          cudaKernel_t kern = nullptr;
+          if (cudaLibraryLoadData(&lib, blob.data() + 4 + nl, nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
+              cudaLibraryGetKernel(&kern, lib, cached_name.c_str()) == cudaSuccess) {
+            api.destroy(&prog);
+            jit_cache_hits()++;
+            return reinterpret_cast<void*>(kern);
+          }
+          cudaGetLastError();  // stale or damaged entry: fall through to a fresh compile, which overwrites it
+        }
+      }
+    }
+  }
   nvrtcResult rc = api.compile(prog, 8, opts);
   if (rc == NVRTC_SUCCESS) {
     size_t sz = 0;
@@ -217,10 +306,19 @@ void* compile_specialised(const JitSpec& sp, bool load = true) {
       cudaLibrary_t lib = nullptr;
       cudaKernel_t kern = nullptr;
       if (cudaLibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == cudaSuccess &&
-          cudaLibraryGetKernel(&kern, lib, lname) == cudaSuccess)
+          cudaLibraryGetKernel(&kern, lib, lname) == cudaSuccess) {
         result = reinterpret_cast<void*>(kern);
-      else
+        if (!cache_path.empty()) {
+          const uint32_t nl = static_cast<uint32_t>(strlen(lname));
+          std::vector<char> blob(4 + nl + sz);
+          memcpy(blob.data(), &nl, 4);
+          memcpy(blob.data() + 4, lname, nl);
+          memcpy(blob.data() + 4 + nl, cubin.data(), sz);
+          write_file_atomic(cache_path, blob.data(), blob.size());
+        }
+      } else {
         cudaGetLastError();
+      }
     }
   } else {
     size_t ls = 0;
@@ -287,6 +385,7 @@ int64_t Engine::jit_compiles() const {
   std::lock_guard<std::mutex> lk(g.mu);
   return g.compiles;
 }
+int64_t Engine::jit_disk_hits() const { return jit_cache_hits().load(); }
 double Engine::jit_seconds() const {
   JitGlobals& g = jit_globals();
   std::lock_guard<std::mutex> lk(g.mu);

@@ -73,6 +73,7 @@ class Engine {
   int64_t jit_compiles() const;  // process-wide
   int64_t jit_launches() const { return jit_launches_; }  // launches of this engine that ran a specialised kernel
   double jit_seconds() const;
+  int64_t jit_disk_hits() const;  // specialised kernels loaded from the on-disk cache instead of compiled (process-wide)
   int num_sms() const { return num_sms_; }
 
  private:

@@ -355,3 +355,31 @@ def test_batcher_merges_concurrent_puts(mb, oracle, pinned):
     assert ei.value.code == -11
     assert all(f.size == 0 for f in bat.encode(b""))
     bat.close()
+
+
+def test_jit_disk_cache_across_processes(tmp_path):
+    """A specialised kernel compiled by one process is loaded from MEC_JIT_CACHE_DIR by the next one (no NVRTC compile)."""
+    import os
+    import subprocess
+    import sys
+    script = r'''
+import sys, json
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np, minio_b200 as mb
+k, m, bs, size = 10, 4, 1 << 20, 6 * (1 << 20) + 99
+d = np.random.default_rng(3).integers(0, 256, size, dtype=np.uint8)
+c = mb.Codec(k, m, bs); c.set_option("jit", 1)
+files = c.encode(d)                                   # RS(10,4) has no compiled kernel: NVRTC-specialised encode
+stale = [i in (1, 12) for i in range(k + m)]
+outs = c.heal([None if stale[i] else files[i] for i in range(k + m)], stale, size)   # and a specialised decode matrix
+ok = all(np.array_equal(outs[i], files[i]) for i in (1, 12))
+print(json.dumps({"ok": bool(ok), "disk_hits": c.stat("jit_disk_hits"), "jit_ms": c.stat("jit_ms"), "jit_launches": c.stat("jit_launches")}))
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, MEC_JIT_CACHE_DIR=str(tmp_path))
+    import json
+    r1 = json.loads(subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, check=True).stdout.strip().split("\n")[-1])
+    assert r1["ok"] and r1["disk_hits"] == 0 and r1["jit_launches"] > 0
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")]) >= 1
+    r2 = json.loads(subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, check=True).stdout.strip().split("\n")[-1])
+    assert r2["ok"] and r2["disk_hits"] >= 1 and r2["jit_launches"] > 0
+    assert r2["jit_ms"] < r1["jit_ms"]
