@@ -268,6 +268,10 @@ int64_t mec_get_stat(const mec_codec* c, const char* name);
  * during an NVRTC compile lets libnvrtc's exit handlers run under the compiling thread); later calls of the library
  * keep working with the kernels already in the cache.  Also registered with atexit() after the first background compile. */
 void mec_shutdown(void);
+/* Queues, on the background compiler, the specialised kernels of every single-missing-data-shard pattern of the codec's geometry
+ * (what a drive failure turns the next GETs and the heal into).  Returns the number of kernels queued; nothing blocks.  With the
+ * on-disk cache this is a one-time cost per (k, m) and library version. */
+int mec_jit_prewarm(mec_codec* c);
 /* Build check of the run-time specialisation (no device needed): NVRTC-compiles the fused kernel for the r x k matrix `coef`
  * (align = S mod 16 of the inputs, eb = erasure blocks per CTA or 0, rows3d / hash_outputs as the engine would pass them)
  * without loading it.  Returns the cubin size, 0 when the compile fails (log in mec_last_error), -1 without libnvrtc. */

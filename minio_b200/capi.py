@@ -91,6 +91,7 @@ def lib():
     L.mec_decode_prefer.argtypes = [vp, vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
     L.mec_jit_compile_check.restype = i64
     L.mec_jit_compile_check.argtypes = [i32, i32, vp, i32, i32, i32, i32]
+    L.mec_jit_prewarm.argtypes = [vp]
     L.mec_shutdown.restype = None
     L.mec_shutdown.argtypes = []
     import atexit

@@ -210,6 +210,33 @@ extern "C" int64_t mec_jit_compile_check(int k, int r, const uint8_t* coef, int 
   return mec::jit_compile_check(k, r, coef, align, eb, rows3d != 0, hash_outputs != 0);
 }
 
+// Pre-warm the kernel cache for the erasure patterns a drive failure will produce: every single missing data shard (the degraded
+// GET of cmd/erasure-decode.go:239 with one drive gone, and the heal of that drive), both CTA shapes.  Compiles run on the
+// background thread (and land in the on-disk cache), nothing waits for them.
+extern "C" int mec_jit_prewarm(mec_codec* c) {
+  if (!c) return MEC_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(c->mu);
+  int rc = ensure_engine(c);
+  if (rc) return rc;
+  const int k = c->k, n = c->n;
+  if (k > kMaxK || n > kMaxShards || c->m < 1) return 0;
+  int queued = 0;
+  for (int miss = 0; miss < k; miss++) {
+    std::vector<uint8_t> present(n, 0), rows(k);
+    int cnt = 0;
+    for (int i = 0; i < n && cnt < k; i++)
+      if (i != miss) { present[i] = 1; cnt++; }
+    int valid[kMaxShards];
+    if (!rs_decode_rows(k, c->m, present.data(), &miss, 1, rows.data(), valid)) continue;
+    for (int eb_t : {4, 0})
+      for (bool hash_out : {false, true}) {
+        c->eng->jit_prewarm(k, 1, rows.data(), eb_t, hash_out);
+        queued++;
+      }
+  }
+  return queued;
+}
+
 extern "C" int64_t mec_launch_count(const mec_codec* c) { return (c && c->eng) ? c->eng->launches() : 0; }
 
 static int require_streaming(mec_codec* c) {

@@ -75,6 +75,10 @@ class Engine {
   double jit_seconds() const;
   int64_t jit_disk_hits() const;  // specialised kernels loaded from the on-disk cache instead of compiled (process-wide)
   int num_sms() const { return num_sms_; }
+  // queue the specialisation of a reconstruct matrix (r x k rows) on the background compiler, as if the pattern were already warm
+  void jit_prewarm(int k, int r, const uint8_t* coef, int eb_t, bool hash_out) {
+    jit_kernel(k, r, coef, 0, eb_t, false, hash_out, -1, int64_t{1} << 40);
+  }
 
  private:
   int device_;

@@ -383,3 +383,31 @@ print(json.dumps({"ok": bool(ok), "disk_hits": c.stat("jit_disk_hits"), "jit_ms"
     r2 = json.loads(subprocess.run([sys.executable, "-c", script], env=env, capture_output=True, text=True, check=True).stdout.strip().split("\n")[-1])
     assert r2["ok"] and r2["disk_hits"] >= 1 and r2["jit_launches"] > 0
     assert r2["jit_ms"] < r1["jit_ms"]
+
+
+def test_jit_prewarm_serves_first_degraded_get(mb, oracle, tmp_path, monkeypatch):
+    """mec_jit_prewarm: after the background compiles finish, the FIRST degraded GET of a single-drive failure already runs a
+    specialised kernel (default jit = -1 would otherwise serve it with the runtime-matrix kernel until 32 MiB have been seen)."""
+    import time
+    k, m, bs, size = 4, 2, MiB, 3 * MiB + 5
+    c = mb.Codec(k, m, bs)
+    queued = mb.lib().mec_jit_prewarm(c.h)
+    assert queued == k * 4
+    c0 = c.stat("jit_compiles")
+    deadline = time.time() + 120
+    while c.stat("jit_compiles") + c.stat("jit_disk_hits") - c0 < 1 and time.time() < deadline:
+        time.sleep(0.2)
+    # wait for the queue to drain: compiles are sequential on one background thread
+    last, stable = -1, 0
+    while stable < 5 and time.time() < deadline:
+        cur = c.stat("jit_compiles")
+        stable = stable + 1 if cur == last else 0
+        last = cur
+        time.sleep(0.5)
+    data = rand(size, 31)
+    files = c.encode(data)
+    j0 = c.stat("jit_launches")
+    out, hint = c.decode([files[0], None] + files[2:], 0, size, size)     # data drive 1 is gone: its first GET
+    assert hint == 0 and np.array_equal(out, data)
+    assert c.stat("jit_launches") > j0
+    c.close()
