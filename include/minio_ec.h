@@ -186,6 +186,11 @@ void mec_batcher_free(mec_batcher* b);
 int64_t mec_batcher_encode(mec_batcher* b, const uint8_t* src, int64_t len, uint8_t* const* files, int write_quorum);
 int64_t mec_batcher_encode_sg(mec_batcher* b, const uint8_t* src, int64_t len, uint8_t* const* files, uint8_t* data_digests,
                               int write_quorum);
+/* Erasure.Decode through the coalescer (arguments and results of mec_decode): GETs queued together that see the same drives online
+ * share one reader set and are merged into one fused launch (gather kernel, reconstruct, scatter into every caller's dst).  A request
+ * that meets a corrupt frame is redone on its own with parallelReader's exact fail-over; pageable buffers take the same private path. */
+int64_t mec_batcher_decode(mec_batcher* b, const uint8_t* const* files, int64_t offset, int64_t length, int64_t total_length,
+                           uint8_t* dst, int* heal_hint);
 int64_t mec_batcher_stat(const mec_batcher* b, const char* name);
 
 /* ---- object checksums of the PutObject stream (internal/hash/checksum.go:64-73, internal/hash/crc.go) ---------------------

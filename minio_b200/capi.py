@@ -66,6 +66,8 @@ def lib():
     L.mec_batcher_encode.argtypes = [vp, vp, i64, vp, i32]
     L.mec_batcher_encode_sg.restype = i64
     L.mec_batcher_encode_sg.argtypes = [vp, vp, i64, vp, vp, i32]
+    L.mec_batcher_decode.restype = i64
+    L.mec_batcher_decode.argtypes = [vp, vp, i64, i64, i64, vp, C.POINTER(i32)]
     L.mec_batcher_stat.restype = i64
     L.mec_batcher_stat.argtypes = [vp, C.c_char_p]
     L.mec_checksums.argtypes = [vp, vp, i64, i32, vp]
@@ -420,6 +422,18 @@ class Batcher:
         if rc < 0:
             raise MecError(rc, "mec_batcher_encode")
         return files
+
+    def decode(self, files, offset, length, total, dst=None):
+        """mec_batcher_decode: files = part-file arrays (None = offline); pass page-locked arrays (and a page-locked dst) to ride in
+        merged launches.  -> (bytes, heal_hint)"""
+        files = [None if f is None else _u8(f) for f in files]
+        if dst is None:
+            dst = np.zeros(max(length, 1), dtype=np.uint8)
+        hint = C.c_int(0)
+        rc = lib().mec_batcher_decode(self.h, _ptrs(files), offset, length, total, dst.ctypes.data, C.byref(hint))
+        if rc < 0:
+            raise MecError(rc, "mec_batcher_decode")
+        return dst[:length], hint.value
 
     def stat(self, name):
         return lib().mec_batcher_stat(self.h, name.encode())

@@ -1768,6 +1768,15 @@ extern "C" int mec_selftest(int device) {
 #include <deque>
 
 struct BatchReq {
+  int kind = 0;                      // 0 = PutObject (encode), 1 = GetObject (decode)
+  // GET
+  const uint8_t* const* gfiles = nullptr;
+  int64_t offset = 0, length = 0, total = 0;
+  uint8_t* dst = nullptr;
+  int* heal_hint = nullptr;
+  uint64_t alive_mask = 0;           // bit i = reader i is online: requests with equal masks share a reader set and a launch
+  int64_t get_slot0 = 0, get_tail_slot = -1, get_nblocks = 0;  // placement of the request's blocks in the merged batch
+  // PUT
   const uint8_t* src = nullptr;
   int64_t len = 0;
   uint8_t* const* files = nullptr;
@@ -1782,6 +1791,8 @@ struct BatchReq {
 
 struct mec_batcher {
   mec_codec* codec = nullptr;
+  mec_codec* serial = nullptr;       // private handle for calls that cannot ride in a batch (pageable buffers, bitrot fail-over)
+  std::mutex serial_mu;
   int64_t max_blocks = 256;
   int max_wait_us = 200;
   std::mutex mu;
@@ -1797,10 +1808,53 @@ struct InflightBatch {
   std::vector<BatchReq*> reqs;
   bool busy = false;
   bool needs_retire = true;  // false: the scatter kernel already assembled the frames
+  bool is_get = false;
+  int get_k = 0;
 };
+
+static mec_codec* batcher_serial(mec_batcher* b) {
+  std::lock_guard<std::mutex> lk(b->serial_mu);
+  if (!b->serial) {
+    mec_codec* c = nullptr;
+    if (mec_codec_new(b->codec->k, b->codec->m, b->codec->block_size, MEC_HIGHWAYHASH256S, b->codec->device, &c) == MEC_OK) b->serial = c;
+  }
+  return b->serial;
+}
 
 static void batcher_finish(mec_batcher* b, InflightBatch& fb, int rc) {
   mec_codec* c = b->codec;
+  if (fb.is_get) {
+    // per-frame digest verdicts of the merged launch: a request that met a corrupt frame is redone on its own through the serial
+    // handle, which applies parallelReader's block-sequential fail-over exactly; the others are done (their bytes are in place)
+    Slot& s = *fb.reqs.front()->ch.s;
+    const uint8_t* fl = static_cast<const uint8_t*>(s.hflags.p);
+    const int k = fb.get_k;
+    for (BatchReq* r : fb.reqs) {
+      int64_t res = rc == MEC_OK ? r->length : rc;
+      if (rc == MEC_OK) {
+        bool bad = false;
+        for (int64_t bb = 0; bb < r->get_nblocks && !bad; bb++) {
+          const int64_t slot = (r->get_tail_slot >= 0 && bb == r->get_nblocks - 1) ? r->get_tail_slot : r->get_slot0 + bb;
+          for (int t = 0; t < k; t++) bad |= fl[slot * k + t] != 0;
+        }
+        if (bad) {
+          mec_codec* sc = batcher_serial(b);
+          res = sc ? mec_decode_prefer(sc, r->gfiles, nullptr, r->offset, r->length, r->total, r->dst, r->heal_hint) : MEC_ERR_UNEXPECTED;
+        } else if (r->heal_hint) {
+          *r->heal_hint = 0;
+        }
+      }
+      r->result = res;
+    }
+    {
+      std::lock_guard<std::mutex> lk(b->mu);
+      for (BatchReq* r : fb.reqs) { r->done = true; r->cv.notify_one(); }
+    }
+    fb.reqs.clear();
+    fb.busy = false;
+    fb.is_get = false;
+    return;
+  }
   for (BatchReq* r : fb.reqs) {
     if (rc == MEC_OK && fb.needs_retire) frames_retire(c, r->ch, r->files, r->with_data, r->data_digests);
     r->result = rc == MEC_OK ? r->len : rc;
@@ -1935,6 +1989,133 @@ static int batcher_submit(mec_batcher* b, Slot& s, std::vector<BatchReq*>& reqs,
   return MEC_OK;
 }
 
+// one merged launch for the GETs of a batch that share a reader set (alive mask): gather kernel -> fused reconstruct over all full
+// blocks (+ one launch per short last block) -> scatter kernel into every caller's destination
+static int batcher_submit_get(mec_batcher* b, Slot& s, std::vector<BatchReq*>& reqs) {
+  mec_codec* c = b->codec;
+  const int k = c->k, n = c->n;
+  const int64_t bs = c->block_size, S = c->S(), P = round_up(32 + S, 16), pitch = round_up(S, 16);
+  // reader set and decode rows of the shared pattern
+  int chosen[kMaxShards], nch = 0;
+  const uint64_t mask = reqs.front()->alive_mask;
+  for (int i = 0; i < n && nch < k; i++)
+    if (mask & (1ull << i)) chosen[nch++] = i;
+  if (nch < k) return MEC_ERR_READ_QUORUM;
+  std::vector<uint8_t> present(n, 0);
+  for (int t = 0; t < k; t++) present[chosen[t]] = 1;
+  int targets[kMaxShards], r = 0;
+  for (int i = 0; i < k; i++)
+    if (!present[i]) targets[r++] = i;
+  if (r > kMaxR) return MEC_ERR_UNSUPPORTED;
+  std::vector<uint8_t> rows(static_cast<size_t>(std::max(r, 1)) * k);
+  int valid[kMaxShards];
+  if (r > 0 && !rs_decode_rows(k, c->m, present.data(), targets, r, rows.data(), valid)) return MEC_ERR_TOO_FEW_SHARDS;
+  // layout: every request's full blocks first, the short last blocks behind them
+  int rc;
+  if ((rc = s.hreq.ensure(reqs.size() * sizeof(BatchGetDesc)))) return rc;
+  if ((rc = s.dreq.ensure(reqs.size() * sizeof(BatchGetDesc)))) return rc;
+  BatchGetDesc* tab = static_cast<BatchGetDesc*>(s.hreq.p);
+  int64_t nfull_slots = 0, ntails = 0, max_nb = 0;
+  for (size_t q = 0; q < reqs.size(); q++) {
+    BatchReq* rq = reqs[q];
+    BatchGetDesc& d = tab[q];
+    memset(&d, 0, sizeof(d));
+    const int64_t sfs = mec_shard_file_size(c, rq->total), nblocks_total = ceil_frac(sfs, S);
+    const int64_t start_block = rq->offset / bs;
+    int64_t last_block = (rq->offset + rq->length) / bs;
+    if ((rq->offset + rq->length) % bs == 0) last_block--;
+    if (last_block >= nblocks_total) last_block = nblocks_total - 1;
+    const int64_t last_len = std::min(S, sfs - last_block * S);
+    d.offset = rq->offset; d.length = rq->length; d.total = rq->total; d.dst = rq->dst;
+    for (int i = 0; i < n; i++) d.files[i] = rq->gfiles[i];
+    d.start_block = start_block; d.nblocks = last_block - start_block + 1;
+    d.last_len = last_len;
+    const bool tail = last_len != S;
+    d.slot0 = nfull_slots;
+    nfull_slots += d.nblocks - (tail ? 1 : 0);
+    d.tail_slot = tail ? ntails : -1;  // provisional: offset by the number of full slots below
+    if (tail) ntails++;
+    max_nb = std::max(max_nb, d.nblocks);
+    rq->get_nblocks = d.nblocks;
+  }
+  static const int64_t dma_blocks = getenv("MEC_BATCHER_DMA_BLOCKS") ? atoll(getenv("MEC_BATCHER_DMA_BLOCKS")) : 8;
+  for (size_t q = 0; q < reqs.size(); q++) {
+    tab[q].dma = tab[q].nblocks >= dma_blocks ? 1 : 0;
+    if (tab[q].tail_slot >= 0) tab[q].tail_slot += nfull_slots;
+    reqs[q]->get_slot0 = tab[q].slot0;
+    reqs[q]->get_tail_slot = tab[q].tail_slot;
+    reqs[q]->ch = EncChunk();
+    reqs[q]->ch.s = &s;
+  }
+  const int64_t nslots = nfull_slots + ntails;
+  const int64_t stride = round_up(nslots * P + 512, 256);
+  if ((rc = s.aux.ensure(static_cast<size_t>(k * stride)))) return rc;
+  if ((rc = s.out.ensure(static_cast<size_t>(nslots * std::max(r, 1) * pitch)))) return rc;
+  if ((rc = s.dig.ensure(static_cast<size_t>(nslots * (k + r) * 32)))) return rc;
+  if ((rc = s.flags.ensure(static_cast<size_t>(nslots * k)))) return rc;
+  if ((rc = s.hflags.ensure(static_cast<size_t>(nslots * k)))) return rc;
+  MEC_CUDA_OK(cudaMemcpyAsync(s.dreq.p, tab, reqs.size() * sizeof(BatchGetDesc), cudaMemcpyHostToDevice, s.st));
+  BatchGetParams gp;
+  memset(&gp, 0, sizeof(gp));
+  gp.reqs = static_cast<const BatchGetDesc*>(s.dreq.p);
+  gp.nreq = static_cast<int>(reqs.size()); gp.k = k; gp.r = r;
+  for (int t = 0; t < k; t++) gp.chosen[t] = chosen[t];
+  for (int q = 0; q < r; q++) gp.targets[q] = targets[q];
+  gp.bs = bs; gp.S = S; gp.P = P;
+  gp.arena = static_cast<uint8_t*>(s.aux.p); gp.arena_stride = stride;
+  gp.rebuilt = static_cast<const uint8_t*>(s.out.p); gp.pitch = pitch;
+  const unsigned gx = static_cast<unsigned>(std::min<int64_t>(std::max<int64_t>(max_nb, 1), 16));
+  // long ranges are staged by the copy engines (k strided copies per request are cheap next to megabytes of frames); short ones by
+  // the gather kernel (no per-request driver call at all)
+  const int64_t fstride = 32 + S;
+  for (size_t q = 0; q < reqs.size(); q++) {
+    const BatchGetDesc& d = tab[q];
+    if (!d.dma) continue;
+    const int64_t nf = d.nblocks - (d.tail_slot >= 0 ? 1 : 0);
+    for (int t = 0; t < k; t++) {
+      const uint8_t* f = d.files[chosen[t]] + d.start_block * fstride;
+      uint8_t* a = gp.arena + t * stride;
+      if (nf > 0)
+        MEC_CUDA_OK(cudaMemcpy2DAsync(a + d.slot0 * P, static_cast<size_t>(P), f, static_cast<size_t>(fstride), static_cast<size_t>(fstride),
+                                      static_cast<size_t>(nf), cudaMemcpyHostToDevice, s.st));
+      if (d.tail_slot >= 0)
+        MEC_CUDA_OK(cudaMemcpyAsync(a + d.tail_slot * P, f + nf * fstride, static_cast<size_t>(32 + d.last_len), cudaMemcpyHostToDevice, s.st));
+    }
+  }
+  batch_get_gather_kernel<<<dim3(gx, static_cast<unsigned>(k), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(gp);
+  MEC_CUDA_OK(cudaGetLastError());
+  c->eng->count_launch();
+  MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(nslots * k), s.st));
+  auto launch = [&](int64_t slot0, int64_t cnt, int64_t shard_len) -> int {
+    FusedDesc d;
+    d.k = k; d.r = r; d.coef = rows.data(); d.static_encode = false; d.contiguous = false; d.hash_outputs = false;
+    d.key = kMagicKey; d.out_pitch = pitch; d.expect_block_stride = P; d.in_block_stride = P;
+    d.nblocks = cnt; d.S = static_cast<int32_t>(shard_len);
+    for (int t = 0; t < k; t++) {
+      const uint8_t* base = gp.arena + t * stride + slot0 * P;
+      d.map_base[t] = base; d.map_len[t] = stride - slot0 * P; d.expect_ptr[t] = base; d.in_ptr[t] = base + 32;
+    }
+    d.out = static_cast<uint8_t*>(s.out.p) + slot0 * r * pitch;
+    d.digests = static_cast<uint8_t*>(s.dig.p) + slot0 * (k + r) * 32;
+    d.corrupt = static_cast<uint8_t*>(s.flags.p) + slot0 * k;
+    return c->eng->launch_fused(d, c->opt, s.st);
+  };
+  if (nfull_slots > 0 && (rc = launch(0, nfull_slots, S))) return rc;  // ONE launch for every caller's full blocks
+  for (size_t q = 0; q < reqs.size(); q++)
+    if (tab[q].tail_slot >= 0 && (rc = launch(tab[q].tail_slot, 1, tab[q].last_len))) return rc;
+  MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(nslots * k), cudaMemcpyDeviceToHost, s.st));
+  batch_get_scatter_kernel<<<dim3(gx, static_cast<unsigned>(k), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(gp);
+  MEC_CUDA_OK(cudaGetLastError());
+  c->eng->count_launch();
+  c->st_blocks_read += nslots;
+  c->st_shards_rebuilt += nslots * r;
+  b->st_batches++;
+  b->st_kernel_batches++;
+  b->st_requests += static_cast<int64_t>(reqs.size());
+  b->st_blocks += nslots;
+  return MEC_OK;
+}
+
 static void batcher_main(mec_batcher* b) {
   mec_codec* c = b->codec;
   cudaSetDevice(c->device);
@@ -1957,13 +2138,16 @@ static void batcher_main(mec_batcher* b) {
         // (measured, profiles/r2_concurrency.md: waiting while batches are in flight only adds latency to a closed loop of callers)
         if (nbusy == 0 && b->max_wait_us > 0 && blocks_queued() < b->max_blocks)
           b->cv_work.wait_for(lk, std::chrono::microseconds(b->max_wait_us), [&] { return b->stop || blocks_queued() >= b->max_blocks; });
+        // a batch = the oldest request plus everything queued behind it of the same kind (and, for GETs, the same reader set)
         int64_t nb = 0;
-        while (!b->queue.empty()) {
-          BatchReq* r = b->queue.front();
-          const int64_t rb = ceil_frac(r->len, c->block_size);
+        const BatchReq* lead = b->queue.front();
+        for (auto it = b->queue.begin(); it != b->queue.end();) {
+          BatchReq* r = *it;
+          if (r->kind != lead->kind || (r->kind == 1 && r->alive_mask != lead->alive_mask)) { ++it; continue; }
+          const int64_t rb = r->kind == 0 ? ceil_frac(r->len, c->block_size) : (r->length / c->block_size + 2);
           if (!reqs.empty() && nb + rb > b->max_blocks) break;
           reqs.push_back(r);
-          b->queue.pop_front();
+          it = b->queue.erase(it);
           nb += rb;
         }
       }
@@ -1973,7 +2157,15 @@ static void batcher_main(mec_batcher* b) {
       int rc;
       {
         std::lock_guard<std::mutex> lk(c->mu);
-        rc = batcher_submit(b, s, reqs, &inflight[head].needs_retire);
+        inflight[head].is_get = reqs.front()->kind == 1;
+        inflight[head].get_k = c->k;
+        if (inflight[head].is_get) {
+          rc = batcher_submit_get(b, s, reqs);
+          if (rc != MEC_OK)
+            for (BatchReq* r : reqs) r->ch.s = &s;  // batcher_finish looks the slot up through the first request
+        } else {
+          rc = batcher_submit(b, s, reqs, &inflight[head].needs_retire);
+        }
       }
       inflight[head].reqs = reqs;
       inflight[head].busy = true;
@@ -2030,6 +2222,7 @@ extern "C" void mec_batcher_free(mec_batcher* b) {
   }
   b->cv_work.notify_all();
   if (b->worker.joinable()) b->worker.join();
+  mec_codec_free(b->serial);
   mec_codec_free(b->codec);
   delete b;
 }
@@ -2064,6 +2257,44 @@ extern "C" int64_t mec_batcher_encode_sg(mec_batcher* b, const uint8_t* src, int
   if (!data_digests) return MEC_ERR_INVALID_ARGUMENT;
   return batcher_call(b, src, len, files, data_digests, false, write_quorum);
 }
+// Erasure.Decode through the coalescer: GETs that are queued together and see the same drives online are merged into one launch.
+// Calls whose buffers are not page-locked, and calls that meet bitrot, run on their own through a private handle.
+extern "C" int64_t mec_batcher_decode(mec_batcher* b, const uint8_t* const* files, int64_t offset, int64_t length, int64_t total,
+                                      uint8_t* dst, int* heal_hint) {
+  if (heal_hint) *heal_hint = 0;
+  if (!b || !files) return MEC_ERR_INVALID_ARGUMENT;
+  if (offset < 0 || length < 0 || offset + length > total) return MEC_ERR_INVALID_ARGUMENT;  // cmd/erasure-decode.go:240-245
+  if (length == 0) return 0;
+  if (!dst) return MEC_ERR_INVALID_ARGUMENT;
+  mec_codec* c = b->codec;
+  const int n = c->n, k = c->k;
+  BatchReq r;
+  r.kind = 1; r.gfiles = files; r.offset = offset; r.length = length; r.total = total; r.dst = dst; r.heal_hint = heal_hint;
+  bool mapped = n <= kBatchMaxFiles && n <= 64 && k <= 32 && mec_is_pinned(dst) != 0;
+  int online = 0;
+  for (int i = 0; i < n; i++) {
+    if (!files[i]) continue;
+    online++;
+    if (i < 64) r.alive_mask |= 1ull << i;
+  }
+  if (online < k) return MEC_ERR_READ_QUORUM;
+  {  // only the k readers that will be used have to be mapped
+    int cnt = 0;
+    for (int i = 0; i < n && cnt < k && mapped; i++)
+      if (files[i]) { mapped = mec_is_pinned(files[i]) != 0; cnt++; }
+  }
+  if (!mapped || getenv("MEC_BATCHER_MEMCPY") != nullptr) {
+    mec_codec* sc = batcher_serial(b);
+    return sc ? mec_decode_prefer(sc, files, nullptr, offset, length, total, dst, heal_hint) : MEC_ERR_UNEXPECTED;
+  }
+  std::unique_lock<std::mutex> lk(b->mu);
+  if (b->stop) return MEC_ERR_INVALID_ARGUMENT;
+  b->queue.push_back(&r);
+  b->cv_work.notify_one();
+  r.cv.wait(lk, [&] { return r.done; });
+  return r.result;
+}
+
 extern "C" int64_t mec_batcher_stat(const mec_batcher* b, const char* name) {
   if (!b || !name) return -1;
   if (!strcmp(name, "batches")) return b->st_batches.load();

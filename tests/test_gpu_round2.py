@@ -411,3 +411,59 @@ def test_jit_prewarm_serves_first_degraded_get(mb, oracle, tmp_path, monkeypatch
     assert hint == 0 and np.array_equal(out, data)
     assert c.stat("jit_launches") > j0
     c.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+def test_batcher_merges_concurrent_gets(mb, oracle, pinned):
+    """Concurrent GETs through one mec_batcher: requests that see the same drives online share a launch; different ranges, sizes with
+    short last blocks, two different failure patterns, and one object with bitrot (redone alone with exact fail-over)."""
+    import threading
+    k, m, bs = 12, 4, MiB
+    sizes = [MiB, 3 * MiB + 4321, 2 * MiB, 100, 5 * MiB + 1, MiB - 1]
+    nthreads, rounds = 24, 4
+    enc = mb.Codec(k, m, bs)
+    bat = mb.Batcher(k, m, bs, max_batch_blocks=128, max_wait_us=2000)
+    mk = (lambda a: (lambda p: (p.__setitem__(slice(None), a), p)[1])(mb.pinned_array(a.size)[:a.size])) if pinned else (lambda a: a)
+    objs = []
+    for t in range(nthreads):
+        d = rand(sizes[t % len(sizes)], 700 + t)
+        files = [mk(f) for f in enc.encode(d)]
+        objs.append((d, files))
+    S = enc.shard_size()
+    # thread 5's object has a corrupt frame on a reader that WILL be used
+    objs[5][1][4][1 * 0 + 40] ^= 0x08
+    errs = []
+
+    def worker(t):
+        d, files = objs[t]
+        n = d.size
+        offline = (0, 3, 13) if t % 4 else (1, 2)          # two failure patterns -> two reader sets
+        fl = [None if i in offline else files[i] for i in range(k + m)]
+        rng = np.random.default_rng(t)
+        try:
+            for it in range(rounds):
+                off = 0 if it == 0 else int(rng.integers(0, n))
+                ln = n - off if it == 0 else int(rng.integers(0, n - off + 1))
+                dst = mb.pinned_array(max(ln, 1))[:max(ln, 1)] if pinned else None
+                out, hint = bat.decode(fl, off, ln, n, dst=dst)
+                if not np.array_equal(out, d[off:off + ln]):
+                    errs.append((t, it, "bytes"))
+                want_hint = -7 if (t == 5 and 4 not in offline and ln > 0 and off < MiB) else 0
+                if t != 5 and hint != 0:
+                    errs.append((t, it, "hint", hint))
+                if t == 5 and it == 0 and hint != want_hint:
+                    errs.append((t, it, "hint5", hint))
+                if pinned and dst is not None:
+                    mb.lib().mec_free_pinned(dst.ctypes.data)
+        except Exception as e:  # noqa: BLE001
+            errs.append((t, repr(e)))
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(nthreads)]
+    [x.start() for x in th]
+    [x.join() for x in th]
+    assert not errs, errs[:6]
+    if pinned:
+        assert bat.stat("kernel_batches") > 0 and bat.stat("batches") < nthreads * rounds
+    with pytest.raises(mb.MecError) as ei:
+        bat.decode([None] * 5 + list(objs[0][1][5:]), 0, 10, objs[0][0].size)
+    assert ei.value.code == -10
+    bat.close(); enc.close()
