@@ -1,12 +1,9 @@
 #!/bin/bash
+# the many-small-concurrent-requests regime on one GPU (profiles/r2_concurrency.md): coalesced vs pooled PUTs and degraded GETs, CPU per-request path
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-O=gpurun_out
-echo "== pytest"; timeout 900 python -m pytest tests/test_gpu_round2.py -q -m gpu -x --timeout 600 -k "batcher" 2>&1 | tail -5
-: > $O/conc.jsonl
-for spec in "batcher 256 1 40" "batcher 1024 1 16" "batcher 256 16 6" "batcher 64 1 80"; do
-  timeout 300 ./tools/conc_bench $spec | tee -a $O/conc.jsonl
+: > gpurun_out/conc.jsonl
+for spec in "batcher 256 1 40" "pool 256 1 40 8" "cpu 128 1 40" "batcher 64 1 80" "batcher 1024 1 16" "batcher 256 4 16" "batcher 256 16 6" "pool 256 16 6 8" "cpu 128 16 6" \
+            "bget 256 1 40" "get 256 1 40 8" "bget 256 4 16" "bget 256 16 6" "get 256 16 6 8"; do
+  timeout 300 ./tools/conc_bench $spec | tee -a gpurun_out/conc.jsonl
 done
-echo "== MAX_WAIT_US=0"; MAX_WAIT_US=0 ./tools/conc_bench batcher 256 1 40
-echo "== MAX_BATCH=128"; MAX_BATCH=128 ./tools/conc_bench batcher 256 1 40
-echo "== 512 threads"; ./tools/conc_bench batcher 512 1 30
