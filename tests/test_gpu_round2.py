@@ -467,3 +467,72 @@ def test_batcher_merges_concurrent_gets(mb, oracle, pinned):
         bat.decode([None] * 5 + list(objs[0][1][5:]), 0, 10, objs[0][0].size)
     assert ei.value.code == -10
     bat.close(); enc.close()
+
+
+def test_full_size_properties_config2_and_3(mb, oracle):
+    """BASELINE.json's full sizes (config 2: 10 GiB stream = 10240 blocks; config 3: 4 shards erased) through size-independent
+    properties: encode -> erase -> reconstruct round trip over EVERY block (rebuilt shards and their digests equal the originals,
+    no frame flagged), linearity of the parity (parity(a ^ b) == parity(a) ^ parity(b)), oracle spot checks at both ends."""
+    import torch
+    k, m, bs, nblocks = 12, 4, MiB, 10240
+    dev = torch.device("cuda:0")
+    S = 87382
+    pitch = (S + 15) // 16 * 16
+    fp = (32 + S + 15) // 16 * 16
+    g = torch.Generator(device=dev); g.manual_seed(0x4D494E494F00 + 2)
+    src = torch.empty(nblocks * bs, dtype=torch.uint8, device=dev)
+    for o0 in range(0, nblocks * bs, 1 << 30):
+        n = min(1 << 30, nblocks * bs - o0)
+        src[o0:o0 + n] = torch.randint(0, 256, (n,), dtype=torch.uint8, device=dev, generator=g)
+    par = torch.zeros((nblocks * m, pitch), dtype=torch.uint8, device=dev)
+    dig = torch.zeros((nblocks, k + m, 32), dtype=torch.uint8, device=dev)
+    c = mb.Codec(k, m, bs)
+    c.set_option("jit", 1)
+    st = torch.cuda.current_stream().cuda_stream
+    c.encode_blocks_device(src.data_ptr(), src.numel(), par.data_ptr(), pitch, dig.data_ptr(), st)
+    torch.cuda.synchronize()
+    for b in (0, nblocks - 1):   # oracle at both ends of the stream
+        sh = oracle.encode_data(k, m, src[b * bs:(b + 1) * bs].cpu().numpy(), fast=True)
+        for j in range(m):
+            assert np.array_equal(par[b * m + j, :S].cpu().numpy(), sh[k + j])
+        for i in range(k + m):
+            assert dig[b, i].cpu().numpy().tobytes() == oracle.hh256(sh[i], fast=True)
+    # linearity on a slice of 256 blocks: GF(2^8) encode is linear over XOR
+    nb2 = 256
+    a, bsl = src[:nb2 * bs], src[4096 * bs:(4096 + nb2) * bs]
+    x = a ^ bsl
+    px = torch.zeros((nb2 * m, pitch), dtype=torch.uint8, device=dev)
+    dx = torch.zeros((nb2, k + m, 32), dtype=torch.uint8, device=dev)
+    c.encode_blocks_device(x.data_ptr(), x.numel(), px.data_ptr(), pitch, dx.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert torch.equal(px[:, :S], par[:nb2 * m, :S] ^ par[4096 * m:(4096 + nb2) * m, :S])
+    del x, px, dx
+    # frames of all 16 drives in one arena, erase {0, 5, 12, 15}, rebuild all four, compare with what was erased
+    arena = torch.zeros((k + m, nblocks, fp), dtype=torch.uint8, device=dev)
+    src2, par3 = src.view(nblocks, bs), par.view(nblocks, m, pitch)
+    for i in range(k + m):
+        arena[i, :, :32] = dig[:, i]
+        if i < k:
+            lo, hi = i * S, min((i + 1) * S, bs)
+            arena[i, :, 32:32 + hi - lo] = src2[:, lo:hi]
+        else:
+            arena[i, :, 32:32 + S] = par3[:, i - k, :S]
+    erased = [0, 5, 12, 15]
+    ptrs = [0 if i in erased else arena[i].data_ptr() for i in range(k + m)]
+    want = [1 if i in erased else 0 for i in range(k + m)]
+    out = torch.zeros((nblocks * 4, pitch), dtype=torch.uint8, device=dev)
+    odig = torch.zeros((nblocks, k + 4, 32), dtype=torch.uint8, device=dev)
+    cor = torch.zeros((nblocks, k), dtype=torch.uint8, device=dev)
+    c.reconstruct_device(ptrs, fp, nblocks, want, 0, out.data_ptr(), pitch, odig.data_ptr(), cor.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert int(cor.sum().item()) == 0
+    o3 = out.view(nblocks, 4, pitch)
+    for q, i in enumerate(erased):
+        assert torch.equal(o3[:, q, :S], arena[i, :, 32:32 + S]), i
+        assert torch.equal(odig[:, k + q], arena[i, :, :32]), i
+    # a single flipped bit anywhere in a survivor is flagged for exactly that frame
+    arena[7, 9999, 32 + 12345] ^= 4
+    c.reconstruct_device(ptrs, fp, nblocks, want, 0, out.data_ptr(), pitch, odig.data_ptr(), cor.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert int(cor.sum().item()) == 1 and int(cor[9999, 5].item()) == 1   # shard 7 is reader position 5 (0 and 5 are offline)
+    c.close()
