@@ -286,7 +286,7 @@ def main():
                 verified &= hd[i].tobytes() == o.hh256(sh[i], fast=True)
 
     # ---- end to end through the C ABI: NUMA-local pinned host buffers, H2D + kernel + D2H inside the timed region
-    e2e = e2e_frames = e2e_decode = host_link = None
+    e2e = e2e_frames = e2e_decode = e2e_verify = host_link = None
     if not args.no_e2e:
         eb = min(args.e2e_blocks, nblocks)
         olen = eb * BS
@@ -346,6 +346,16 @@ def main():
                       "call": "mec_decode (Erasure.Decode, data drives 0-3 offline: 12 survivor part files in, digests verified, 4 shards rebuilt, object bytes out by DMA)"}
         if oracle_leg and verified:
             verified &= bool(np.array_equal(h_dst, h_src))
+        # deep scan (bitrotVerify of every part file of the object, cmd/bitrot.go:164): hash + compare only, one byte in per byte scanned
+        nfl = K + M
+        fl_arr = (C.c_int64 * nfl)(*[fsz] * nfl); pl_arr = (C.c_int64 * nfl)(*[codec.shard_file_size(olen)] * nfl); res_arr = (C.c_int32 * nfl)()
+
+        def verify_step():
+            rc = L.mec_bitrot_verify_batch(codec.h, nfl, fp_all, fl_arr, pl_arr, res_arr)
+            assert rc == 0 and not any(res_arr), (rc, list(res_arr))
+        dt = timed(verify_step, max(reps // 2, 3))
+        e2e_verify = {"value": world * nfl * fsz * max(reps // 2, 3) / GiB / dt, "unit": "GiB/s of part-file bytes scanned", "h2d_bytes_per_step": nfl * fsz, "d2h_bytes_per_step": nfl * eb,
+                      "call": "mec_bitrot_verify_batch (deep scan of all 16 part files of the object; every frame's HighwayHash recomputed and compared)"}
         # what the link itself gives: pinned H2D alone, then H2D and D2H together (the pattern of the calls above)
         d_a = torch.empty(1 << 30, dtype=torch.uint8, device=dev); d_b = torch.empty(1 << 28, dtype=torch.uint8, device=dev)
         t_src = torch.from_numpy(h_src[:1 << 30]); t_dst = torch.from_numpy(h_dst[:1 << 28])
@@ -439,7 +449,7 @@ def main():
         "alu_roofline": {"achieved_lane_ops_per_s": alu_rate, "peak_lane_ops_per_s": alu_peak, "frac": alu_rate / alu_peak,
                          "alu_warp_instr_per_tile_block": ALU_WARP_INSTR_PER_TILE_BLOCK,
                          "note": "the kernel is bound by the integer ALU pipe (64 lanes/clk/SM), not by HBM: this is the pipe's busy fraction from instruction counts"},
-        "e2e": e2e, "e2e_frames": e2e_frames, "e2e_decode": e2e_decode, "host_link": host_link,
+        "e2e": e2e, "e2e_frames": e2e_frames, "e2e_decode": e2e_decode, "e2e_verify": e2e_verify, "host_link": host_link,
         "gpu_launches": int(launches), "clocks": clocks, "verified_vs_oracle": verified,
     }
     if configs is not None:

@@ -242,6 +242,11 @@ int mec_digest_size(int algo);
 
 /* bitrotVerify (cmd/bitrot.go:164) for the streaming algorithm: scans a whole shard file. */
 int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file_len, int64_t part_len);
+/* The same for many shard files at once (the deep scan of the data scanner visits every part on every drive): results[f] = MEC_OK or
+ * MEC_ERR_FILE_CORRUPT (wrong length or a frame that fails its digest); the frames of all files stream through the codec's slots and
+ * consecutive full frames — across files — share one hash-only launch.  Returns MEC_OK unless the call itself failed. */
+int mec_bitrot_verify_batch(mec_codec* c, int64_t nfiles, const uint8_t* const* files, const int64_t* file_lens,
+                            const int64_t* part_lens, int* results);
 
 /* ---- shard-shaped low-level calls (keep Erasure.EncodeData / reedsolomon.Encoder shapes) ---- */
 /* reedsolomon.Encoder.Encode: shards[0..k) in, shards[k..k+m) out, each shard_len bytes (host). */

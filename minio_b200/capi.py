@@ -101,6 +101,7 @@ def lib():
     L.mec_get_stat.restype = i64
     L.mec_get_stat.argtypes = [vp, C.c_char_p]
     L.mec_bitrot_verify.argtypes = [vp, vp, i64, i64]
+    L.mec_bitrot_verify_batch.argtypes = [vp, i64, vp, vp, vp, vp]
     L.mec_encode_whole.restype = i64
     L.mec_encode_whole.argtypes = [vp, vp, i64, vp, vp, i32]
     L.mec_whole_hash.argtypes = [vp, i32, vp, i64, i64, vp]
@@ -300,6 +301,18 @@ class Codec:
     def bitrot_verify(self, file, part_len):
         f = _u8(file)
         return lib().mec_bitrot_verify(self.h, f.ctypes.data if f.size else None, f.size, part_len)
+
+    def bitrot_verify_batch(self, files, part_lens):
+        """mec_bitrot_verify_batch: -> list of 0 / -7 per shard file."""
+        files = [_u8(f) for f in files]
+        n = len(files)
+        fl = (C.c_int64 * n)(*[f.size for f in files])
+        pl = (C.c_int64 * n)(*[int(x) for x in part_lens])
+        res = (C.c_int32 * n)()
+        rc = lib().mec_bitrot_verify_batch(self.h, n, _ptrs(files), fl, pl, res)
+        if rc:
+            raise MecError(rc, "mec_bitrot_verify_batch")
+        return list(res)
 
     # -- legacy whole-file bitrot
     def encode_whole(self, src, online=None, write_quorum=0):

@@ -1116,46 +1116,114 @@ extern "C" int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobject
   return first_err.load();
 }
 
-extern "C" int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file_len, int64_t part_len) {
-  if (!c || !file) return MEC_ERR_INVALID_ARGUMENT;
+// bitrotVerify (cmd/bitrot.go:164-215), streaming algorithm: every frame's digest is recomputed and compared.  The scan of one
+// or many shard files (the scanner's deep-scan visits every part of every drive of an object: cmd/xl-storage.go:2550-2600) is cut
+// into chunks of frames that run through the codec's slots: staging of chunk c+1 overlaps the hash-only launch (k = 1, r = 0) of
+// chunk c; a chunk's verdicts come back when its slot is reused.  result[f] = MEC_OK / MEC_ERR_FILE_CORRUPT per file.
+static int verify_files_locked(mec_codec* c, int64_t nfiles, const uint8_t* const* files, const int64_t* file_lens, const int64_t* part_lens,
+                               int* results) {
+  const int64_t S = c->S(), fstride = 32 + S, P = round_up(32 + S, 16);
+  MEC_CUDA_OK(cudaSetDevice(c->device));
+  struct Drain { mec_codec* c; ~Drain() { for (auto& s : c->slots) if (s.st) cudaStreamSynchronize(s.st); } } drain{c};
+  struct Piece { int64_t file, nb; };
+  std::vector<Piece> inflight[kSlots];
+  const int64_t chunk = std::max<int64_t>(1, (32ll << 20) / fstride);  // frames per chunk (~32 MiB)
+  int rc;
+  auto retire = [&](int si) {
+    const uint8_t* fl = static_cast<const uint8_t*>(c->slots[si].hflags.p);
+    int64_t o = 0;
+    for (const Piece& pc : inflight[si]) {
+      for (int64_t b = 0; b < pc.nb; b++)
+        if (fl[o + b]) results[pc.file] = MEC_ERR_FILE_CORRUPT;
+      o += pc.nb;
+    }
+    inflight[si].clear();
+  };
+  int si = 0;
+  int64_t f = 0, b0 = 0;  // next file / next frame of it
+  while (f < nfiles) {
+    Slot& s = c->slots[si];
+    MEC_CUDA_OK(cudaStreamSynchronize(s.st));
+    retire(si);
+    if ((rc = s.src.ensure(static_cast<size_t>(chunk * P + 512)))) return rc;
+    if ((rc = s.dig.ensure(static_cast<size_t>(chunk * 32)))) return rc;
+    if ((rc = s.flags.ensure(static_cast<size_t>(chunk)))) return rc;
+    if ((rc = s.hflags.ensure(static_cast<size_t>(chunk)))) return rc;
+    MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(chunk), s.st));
+    int64_t used = 0;
+    // fill the chunk with frames of consecutive files; full frames of all of them hash in ONE launch, short last frames one each
+    struct Tail { int64_t slot, len; };
+    std::vector<Tail> tails;
+    while (f < nfiles && used < chunk) {
+      if (results[f] != MEC_OK || part_lens[f] == 0) { f++; b0 = 0; continue; }
+      const int64_t nblocks = ceil_frac(part_lens[f], S), last_len = part_lens[f] - (nblocks - 1) * S;
+      const int64_t take = std::min(chunk - used, nblocks - b0);
+      FrameGeom sub{take, S, (b0 + take == nblocks) ? last_len : S};
+      if ((rc = stage_frames(files[f] + b0 * fstride, static_cast<uint8_t*>(s.src.p) + used * P, sub, s.st))) return rc;
+      c->st_h2d += sub.file_bytes();
+      if (sub.last_len != S) tails.push_back(Tail{used + take - 1, sub.last_len});
+      inflight[si].push_back(Piece{f, take});
+      used += take;
+      b0 += take;
+      if (b0 == nblocks) { f++; b0 = 0; }
+    }
+    if (used == 0) break;
+    auto launch = [&](int64_t slot0, int64_t cnt, int64_t len) -> int {
+      FusedDesc d;
+      d.k = 1; d.r = 0; d.contiguous = false; d.key = kMagicKey;
+      d.in_block_stride = P; d.expect_block_stride = P;
+      const uint8_t* base = static_cast<const uint8_t*>(s.src.p) + slot0 * P;
+      d.nblocks = cnt; d.S = static_cast<int32_t>(len);
+      d.map_base[0] = base; d.map_len[0] = (chunk - slot0) * P + 512;
+      d.expect_ptr[0] = base; d.in_ptr[0] = base + 32;
+      d.digests = static_cast<uint8_t*>(s.dig.p) + slot0 * 32;
+      d.corrupt = static_cast<uint8_t*>(s.flags.p) + slot0;
+      return c->eng->launch_fused(d, c->opt, s.st);
+    };
+    // runs of full frames between the short ones (a short frame's digest covers fewer bytes: its own launch)
+    int64_t at = 0;
+    for (size_t q = 0; q <= tails.size(); q++) {
+      const int64_t end = q < tails.size() ? tails[q].slot : used;
+      if (end > at && (rc = launch(at, end - at, S))) return rc;
+      if (q < tails.size()) {
+        if ((rc = launch(tails[q].slot, 1, tails[q].len))) return rc;
+        at = tails[q].slot + 1;
+      }
+    }
+    MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(used), cudaMemcpyDeviceToHost, s.st));
+    c->st_blocks_read += used;
+    si = (si + 1) % kSlots;
+  }
+  for (int q = 0; q < kSlots; q++, si = (si + 1) % kSlots) {
+    MEC_CUDA_OK(cudaStreamSynchronize(c->slots[si].st));
+    retire(si);
+  }
+  return MEC_OK;
+}
+
+extern "C" int mec_bitrot_verify_batch(mec_codec* c, int64_t nfiles, const uint8_t* const* files, const int64_t* file_lens,
+                                       const int64_t* part_lens, int* results) {
+  if (!c || nfiles < 0 || (nfiles > 0 && (!files || !file_lens || !part_lens || !results))) return MEC_ERR_INVALID_ARGUMENT;
   const int64_t S = c->S();
-  if (file_len != mec_bitrot_shard_file_size(part_len, S, c->algo)) return MEC_ERR_FILE_CORRUPT;  // cmd/bitrot.go:183
-  if (part_len == 0) return MEC_OK;
+  bool any = false;
+  for (int64_t f = 0; f < nfiles; f++) {
+    results[f] = MEC_OK;
+    if (!files[f] && part_lens[f] > 0) { results[f] = MEC_ERR_INVALID_ARGUMENT; continue; }
+    if (file_lens[f] != mec_bitrot_shard_file_size(part_lens[f], S, c->algo)) results[f] = MEC_ERR_FILE_CORRUPT;  // cmd/bitrot.go:183
+    else if (part_lens[f] > 0) any = true;
+  }
+  if (!any) return MEC_OK;
   int rc = require_streaming(c);
   if (rc) return rc;
   std::lock_guard<std::mutex> lk(c->mu);
-  MEC_CUDA_OK(cudaSetDevice(c->device));
-  Slot& s = c->slots[0];
-  const int64_t nblocks = ceil_frac(part_len, S), last_len = part_len - (nblocks - 1) * S;
-  FrameGeom g{nblocks, S, last_len};
-  const int64_t P = g.dpitch();
-  if ((rc = s.src.ensure(static_cast<size_t>(g.dev_bytes())))) return rc;
-  if ((rc = s.dig.ensure(static_cast<size_t>(nblocks * 32)))) return rc;
-  if ((rc = c->flags.ensure(static_cast<size_t>(nblocks)))) return rc;
-  if ((rc = stage_frames(file, s.src.p, g, s.st))) return rc;
-  MEC_CUDA_OK(cudaMemsetAsync(c->flags.p, 0, static_cast<size_t>(nblocks), s.st));
-  FusedDesc d;
-  d.k = 1; d.r = 0; d.contiguous = false; d.key = kMagicKey;
-  d.in_block_stride = P; d.expect_block_stride = P;
-  const uint8_t* base = static_cast<const uint8_t*>(s.src.p);
-  const int64_t nfull = last_len == S ? nblocks : nblocks - 1;
-  for (int pass = 0; pass < 2; pass++) {
-    const int64_t first = pass == 0 ? 0 : nfull, nb = pass == 0 ? nfull : nblocks - nfull;
-    if (nb <= 0) continue;
-    d.nblocks = nb; d.S = static_cast<int32_t>(pass == 0 ? S : last_len);
-    d.map_base[0] = base + first * P; d.map_len[0] = g.dev_bytes() - first * P;
-    d.expect_ptr[0] = base + first * P;
-    d.in_ptr[0] = base + first * P + 32;
-    d.digests = static_cast<uint8_t*>(s.dig.p) + first * 32;
-    d.corrupt = static_cast<uint8_t*>(c->flags.p) + first;
-    if ((rc = c->eng->launch_fused(d, c->opt, s.st))) return rc;
-  }
-  std::vector<uint8_t> flags(static_cast<size_t>(nblocks));
-  MEC_CUDA_OK(cudaMemcpyAsync(flags.data(), c->flags.p, flags.size(), cudaMemcpyDeviceToHost, s.st));
-  MEC_CUDA_OK(cudaStreamSynchronize(s.st));
-  for (auto f : flags)
-    if (f) return MEC_ERR_FILE_CORRUPT;
-  return MEC_OK;
+  return verify_files_locked(c, nfiles, files, file_lens, part_lens, results);
+}
+
+extern "C" int mec_bitrot_verify(mec_codec* c, const uint8_t* file, int64_t file_len, int64_t part_len) {
+  if (!c || !file) return MEC_ERR_INVALID_ARGUMENT;
+  int result = MEC_OK;
+  const int rc = mec_bitrot_verify_batch(c, 1, &file, &file_len, &part_len, &result);
+  return rc ? rc : result;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -536,3 +536,29 @@ def test_full_size_properties_config2_and_3(mb, oracle):
     torch.cuda.synchronize()
     assert int(cor.sum().item()) == 1 and int(cor[9999, 5].item()) == 1   # shard 7 is reader position 5 (0 and 5 are offline)
     c.close()
+
+
+def test_bitrot_verify_batch_deep_scan(mb, oracle):
+    """Deep scan of every part file of several objects in one call (pipelined chunks, launches shared across files): good files,
+    a flipped data byte, a flipped digest byte, a truncated file, an empty part; against the oracle's bitrotVerify."""
+    k, m, bs = 12, 4, MiB
+    c = mb.Codec(k, m, bs)
+    S = c.shard_size()
+    files, plens, want = [], [], []
+    for size, seed in ((40 * MiB + 777, 1), (MiB, 2), (3 * MiB + 5, 3), (100, 4)):
+        d = rand(size, 600 + seed)
+        fs = c.encode(d)
+        for i in range(k + m):
+            files.append(fs[i]); plens.append(c.shard_file_size(size)); want.append(0)
+    bad = [f.copy() for f in files]
+    bad[3][17 * (32 + S) + 32 + 99] ^= 1; want[3] = -7           # data byte of frame 17
+    bad[20][5] ^= 0x10; want[20] = -7                             # digest byte of the only frame of a 1 MiB object's shard
+    bad[40] = bad[40][:-1].copy(); want[40] = -7                  # wrong length (cmd/bitrot.go:183)
+    bad[50][bad[50].size - 1] ^= 0x80; want[50] = -7              # last byte of a short last frame
+    got = c.bitrot_verify_batch(bad, plens)
+    assert got == want
+    for i in (0, 3, 20, 50):
+        assert oracle.bitrot_verify(oracle.HIGHWAYHASH256S, bad[i], plens[i], S) == want[i]
+        assert c.bitrot_verify(bad[i], plens[i]) == want[i]
+    assert c.bitrot_verify_batch([np.zeros(0, dtype=np.uint8)], [0]) == [0]
+    c.close()
