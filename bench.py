@@ -463,7 +463,18 @@ def main():
         gib1, sec1 = arm.run()
         reps = max(1, int(10.0 / max(sec1, 1e-3)))
         gib, sec = arm.run(reps)
-        out["cpu_baseline"] = {"value": gib, "unit": "GiB/s", "cores": arm.threads, "kind": "port",
+        split = {}
+        for mode, name in ((1, "encode_only_GiB_per_s"), (2, "hash_only_GiB_per_s")):   # the two passes apart
+            arm.L.orc_pool_set_mode(mode)
+            arm.run()
+            split[name] = arm.run(max(1, reps // 8))[0]
+        arm.L.orc_pool_set_mode(0)
+        model = ""
+        try:
+            model = [l.split(":", 1)[1].strip() for l in open("/proc/cpuinfo") if l.startswith("model name")][0]
+        except Exception:
+            pass
+        out["cpu_baseline"] = {"value": gib, "unit": "GiB/s", "cores": arm.threads, "kind": "port", "cpu_model": model, **split,
                                "sample": arm.describe(f"{reps} passes = {sec:.1f} s")}
         arm.close()
     print(json.dumps(out))

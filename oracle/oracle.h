@@ -153,6 +153,7 @@ void orc_pool_fill(orc_pool *p, int k, int m, int64_t block_size, uint8_t *src, 
 double orc_pool_encode_hash(orc_pool *p, int k, int m, int64_t block_size, const uint8_t *src, int64_t nblocks, uint8_t *parity,
                             uint8_t *digests, int reps);
 void orc_pool_free(orc_pool *p);
+void orc_pool_set_mode(int mode); /* 0 = encode + hash, 1 = encode only, 2 = hash only */
 
 #ifdef __cplusplus
 }

@@ -160,6 +160,7 @@ void orc_hh256_fast(const uint8_t key[32], const uint8_t *p, size_t n, uint8_t o
 }
 
 /* ---------------- multi-threaded encode + hash over independent blocks ---------------- */
+static int g_mt_mode = 0; /* 0 = encode + hash, 1 = encode only, 2 = hash only (bench legs; set between runs, never during one) */
 typedef struct {
   int k, m, tid, threads, reps;
   int64_t bs, nblocks;
@@ -185,9 +186,10 @@ static void *mt_worker(void *vp) {
         sh[k - 1] = last;
       }
       for (int j = 0; j < m; j++) sh[k + j] = a->parity + ((size_t)b * m + j) * S;
-      rs_rows(a->rows, k, m, sh, sh + k, S);                       /* pass 1: Encode */
-      for (int i = 0; i < n; i++)                                    /* pass 2: bitrot hash per shard */
-        orc_hh256_fast(orc_magic_hh_key, sh[i], (size_t)S, a->digests + ((size_t)b * n + i) * 32);
+      if (g_mt_mode != 2) rs_rows(a->rows, k, m, sh, sh + k, S);   /* pass 1: Encode */
+      if (g_mt_mode != 1)
+        for (int i = 0; i < n; i++)                                  /* pass 2: bitrot hash per shard */
+          orc_hh256_fast(orc_magic_hh_key, sh[i], (size_t)S, a->digests + ((size_t)b * n + i) * 32);
     }
   free(last); free(sh);
   return NULL;
@@ -357,3 +359,6 @@ void orc_pool_free(orc_pool *p) {
   for (int t = 0; t < p->threads; t++) pthread_join(p->th[t], NULL);
   free(p->th); free(p->w); free(p);
 }
+
+/* which passes the workers run: 0 = RS encode + HighwayHash (the reference's work), 1 = encode only, 2 = hash only */
+void orc_pool_set_mode(int mode) { g_mt_mode = mode; }
