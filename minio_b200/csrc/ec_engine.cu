@@ -699,9 +699,20 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   }
   const size_t smem = fused_smem_bytes(d.k, d.r, eb, p.raw_pitch, se == nullptr && !jitted, direct);
   if (smem > 227 * 1024) return MEC_ERR_UNSUPPORTED;
-  MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  // the attribute and the occupancy query cost ~10 us of driver time per launch — a third of a small object's latency: remembered
+  // per (kernel, CTA shape, shared memory)
   int per_sm = 0;
-  MEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+  {
+    bool hit = false;
+    for (const LaunchMemo& lm : launch_memo_)
+      if (lm.fn == kfn && lm.threads == threads && lm.smem == smem) { per_sm = lm.per_sm; hit = true; break; }
+    if (!hit) {
+      MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      MEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
+      if (launch_memo_.size() >= 64) launch_memo_.clear();
+      launch_memo_.push_back(LaunchMemo{kfn, threads, smem, per_sm});
+    }
+  }
   if (per_sm < 1) per_sm = 1;
   if (opt.grid_mult > 0 && opt.grid_mult < per_sm) per_sm = opt.grid_mult;
   const int64_t ngroups = (d.nblocks + eb - 1) / eb;

@@ -86,6 +86,8 @@ class Engine {
   void* encode_tiled_ = nullptr;  // cuTensorMapEncodeTiled
   int64_t launches_ = 0;
   int64_t jit_launches_ = 0;
+  struct LaunchMemo { const void* fn; int threads; size_t smem; int per_sm; };
+  std::vector<LaunchMemo> launch_memo_;
   uint32_t* claim_slots_ = nullptr;  // ring of per-launch group-claim counters (device)
   uint32_t claim_next_ = 0;
   // run-time specialised kernels, keyed by (k, r, matrix bytes)
