@@ -177,9 +177,11 @@ int mec_heal_batch(mec_codec* const* pool, int npool, int64_t nobjects, const ui
  * cmd/erasure-object.go:1371); a launch that small leaves 147 of 148 SMs idle.  A batcher owns one codec (k, m, block_size,
  * HighwayHash256S) and a worker thread: callers block in mec_batcher_encode / mec_batcher_encode_sg (same arguments and results
  * as mec_encode / mec_encode_sg), the worker merges everything that is queued — up to max_batch_blocks erasure blocks, waiting
- * at most max_wait_us for company when the GPU is idle — into one staged buffer and ONE fused launch over all full blocks, then
- * DMA-copies every caller's frames straight into that caller's buffers.  Up to three merged batches are in flight.
- * mec_batcher_stat: "batches", "requests", "blocks", "launches". */
+ * at most max_wait_us for company when the GPU is idle — into one staged buffer (one batched copy call) and ONE fused launch over
+ * all full blocks, then writes every caller's frames straight into that caller's buffers.  Up to six merged batches are in flight;
+ * device staging for all six is allocated here (about 2.4 x max_batch_blocks x block_size each).
+ * mec_batcher_stat: "batches", "requests", "blocks", "launches"; with MEC_BATCHER_TRACE=1 in the environment also the worker's and the
+ * streams' accumulated phase times "us_submit", "us_sync", "us_finish", "us_idle", "us_stage", "us_kernel", "us_scatter". */
 typedef struct mec_batcher mec_batcher;
 int mec_batcher_new(int k, int m, int64_t block_size, int device, int64_t max_batch_blocks, int max_wait_us, mec_batcher** out);
 void mec_batcher_free(mec_batcher* b);

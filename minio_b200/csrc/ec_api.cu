@@ -1869,6 +1869,14 @@ struct mec_batcher {
   bool stop = false;
   std::thread worker;
   std::atomic<int64_t> st_batches{0}, st_requests{0}, st_blocks{0}, st_kernel_batches{0};
+  // hybrid staging: part of a batch is read by the gather kernel on `aux` while the copy engine moves the rest
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_table[kSlots] = {}, ev_gather[kSlots] = {};
+  int gather_pct = 0;
+  // where the worker's time and each batch's stream time go (mec_batcher_stat "us_*"); device phases need MEC_BATCHER_TRACE=1
+  bool trace = false;
+  cudaEvent_t ev_ph[kSlots][4] = {};
+  std::atomic<int64_t> us_submit{0}, us_sync{0}, us_finish{0}, us_idle{0}, us_stage{0}, us_kernel{0}, us_scatter{0};
 };
 
 namespace {
@@ -1877,6 +1885,7 @@ struct InflightBatch {
   bool busy = false;
   bool needs_retire = true;  // false: the scatter kernel already assembled the frames
   bool is_get = false;
+  bool traced = false;
   int get_k = 0;
 };
 
@@ -1935,6 +1944,22 @@ static void batcher_finish(mec_batcher* b, InflightBatch& fb, int rc) {
   fb.busy = false;
 }
 
+// a train of independent copies as one driver call (CUDA 12.8 cudaMemcpyBatchAsync); MEC_NO_BATCH_COPY=1: one call per copy
+static int copy_batch(std::vector<void*>& dsts, std::vector<void*>& srcs, std::vector<size_t>& sizes, cudaStream_t st) {
+  if (dsts.empty()) return MEC_OK;
+  static const bool no_batch = getenv("MEC_NO_BATCH_COPY") != nullptr;
+  if (!no_batch && dsts.size() > 1) {
+    cudaMemcpyAttributes at = {};
+    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t idx0 = 0, fail = 0;
+    const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, st);
+    if (e == cudaSuccess) return MEC_OK;
+    cudaGetLastError();  // older driver: fall through to separate calls
+  }
+  for (size_t i = 0; i < dsts.size(); i++) MEC_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, st));
+  return MEC_OK;
+}
+
 // stage, launch and enqueue the copy-back of one merged batch on slot `s`
 static int batcher_submit(mec_batcher* b, Slot& s, std::vector<BatchReq*>& reqs, bool* needs_retire) {
   mec_codec* c = b->codec;
@@ -1984,6 +2009,8 @@ static int batcher_submit(mec_batcher* b, Slot& s, std::vector<BatchReq*>& reqs,
       c->st_h2d += r->len;
       c->st_d2h += (nf * S + (tl ? ceil_frac(tl, k) : 0)) * (r->with_data ? n : m);
     }
+    const int phase_slot = static_cast<int>(&s - c->slots);
+    if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][0], s.st);
     MEC_CUDA_OK(cudaMemcpyAsync(s.dreq.p, tab, reqs.size() * sizeof(BatchReqDesc), cudaMemcpyHostToDevice, s.st));
     BatchCopyParams cp;
     cp.reqs = static_cast<const BatchReqDesc*>(s.dreq.p);
@@ -1992,28 +2019,53 @@ static int batcher_submit(mec_batcher* b, Slot& s, std::vector<BatchReq*>& reqs,
     // staging: the copy engines are the faster reader of host memory (one call per request); the gather kernel (SM loads over
     // PCIe, no per-request call at all) is kept for hosts where the worker thread is the bottleneck — measured in profiles/r2_concurrency.md
     static const bool use_gather = getenv("MEC_BATCHER_GATHER") != nullptr;
-    if (use_gather) {
-      const unsigned gx = static_cast<unsigned>(std::min<int64_t>(64, std::max<int64_t>(1, ceil_frac(max_len, 32 << 10))));
-      batch_gather_kernel<<<dim3(gx, static_cast<unsigned>(reqs.size())), 256, 0, s.st>>>(cp);
+    // requests [0, ndma) go through the copy engine, [ndma, nreq) through the gather kernel on the aux stream, concurrently
+    size_t ndma = use_gather ? 0 : reqs.size();
+    if (!use_gather && b->gather_pct > 0 && b->aux && reqs.size() >= 8)
+      ndma = reqs.size() - reqs.size() * static_cast<size_t>(b->gather_pct) / 100;
+    if (ndma < reqs.size()) {
+      const int si = static_cast<int>(&s - c->slots);
+      cudaStream_t gs = s.st;
+      if (ndma > 0) {
+        gs = b->aux;
+        MEC_CUDA_OK(cudaEventRecord(b->ev_table[si], s.st));
+        MEC_CUDA_OK(cudaStreamWaitEvent(gs, b->ev_table[si], 0));
+      }
+      int64_t glen = 0;
+      for (size_t q = ndma; q < reqs.size(); q++) glen = std::max(glen, tab[q].len);
+      BatchCopyParams gp = cp;
+      gp.reqs = cp.reqs + ndma;
+      gp.nreq = static_cast<int>(reqs.size() - ndma);
+      const unsigned gx = static_cast<unsigned>(std::min<int64_t>(64, std::max<int64_t>(1, ceil_frac(glen, 32 << 10))));
+      batch_gather_kernel<<<dim3(gx, static_cast<unsigned>(gp.nreq)), 256, 0, gs>>>(gp);
       MEC_CUDA_OK(cudaGetLastError());
       c->eng->count_launch();
-    } else {
-      for (size_t q = 0; q < reqs.size(); q++) {
+      if (ndma > 0) MEC_CUDA_OK(cudaEventRecord(b->ev_gather[si], gs));
+    }
+    {
+      // ONE cudaMemcpyBatchAsync for the whole batch: the copy engine runs a train of 1 MiB pieces at the link rate (55 GB/s) where
+      // the same pieces as separate cudaMemcpyAsync calls reach 40-46 GB/s (tools/copy_probe.cu, profiles/r2_concurrency.md)
+      std::vector<void*> dsts, srcs;
+      std::vector<size_t> sizes;
+      for (size_t q = 0; q < ndma; q++) {
         const BatchReqDesc& d = tab[q];
         const int64_t fbytes = d.len / bs * bs, tl = d.len - fbytes;
-        cudaStream_t cs = s.st;  // (spreading the copies over a second stream / copy engine was measured: no gain)
-        if (fbytes > 0) MEC_CUDA_OK(cudaMemcpyAsync(dsrc + d.full0 * bs, d.src, static_cast<size_t>(fbytes), cudaMemcpyHostToDevice, cs));
-        if (tl > 0) MEC_CUDA_OK(cudaMemcpyAsync(dsrc + d.tail_src_off, d.src + fbytes, static_cast<size_t>(tl), cudaMemcpyHostToDevice, cs));
+        if (fbytes > 0) { dsts.push_back(dsrc + d.full0 * bs); srcs.push_back(const_cast<uint8_t*>(d.src)); sizes.push_back(static_cast<size_t>(fbytes)); }
+        if (tl > 0) { dsts.push_back(dsrc + d.tail_src_off); srcs.push_back(const_cast<uint8_t*>(d.src) + fbytes); sizes.push_back(static_cast<size_t>(tl)); }
       }
-
+      if ((rc = copy_batch(dsts, srcs, sizes, s.st))) return rc;
     }
+    if (ndma > 0 && ndma < reqs.size()) MEC_CUDA_OK(cudaStreamWaitEvent(s.st, b->ev_gather[static_cast<int>(&s - c->slots)], 0));
+    if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][1], s.st);
     if (total_full > 0 && (rc = encode_device_locked(c, dsrc, total_full * bs, dout, pitch, ddig, s.st))) return rc;
     for (BatchReq* r : reqs)
       if (r->ch.tail > 0 && (rc = encode_device_locked(c, r->ch.d_src_tail, r->ch.tail, r->ch.d_out_tail, pitch, ddig + (r->ch.h_dig_tail - hdig), s.st)))
         return rc;
+    if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][2], s.st);
     batch_scatter_kernel<<<dim3(static_cast<unsigned>(std::min<int64_t>(max_nb, 16)), static_cast<unsigned>(n), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(cp);
     MEC_CUDA_OK(cudaGetLastError());
     c->eng->count_launch();
+    if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][3], s.st);
     *needs_retire = false;
     c->st_blocks_encoded += nslots;
     b->st_batches++;
@@ -2106,7 +2158,7 @@ static int batcher_submit_get(mec_batcher* b, Slot& s, std::vector<BatchReq*>& r
     max_nb = std::max(max_nb, d.nblocks);
     rq->get_nblocks = d.nblocks;
   }
-  static const int64_t dma_blocks = getenv("MEC_BATCHER_DMA_BLOCKS") ? atoll(getenv("MEC_BATCHER_DMA_BLOCKS")) : 8;
+  static const int64_t dma_blocks = getenv("MEC_BATCHER_DMA_BLOCKS") ? atoll(getenv("MEC_BATCHER_DMA_BLOCKS")) : 1;
   for (size_t q = 0; q < reqs.size(); q++) {
     tab[q].dma = tab[q].nblocks >= dma_blocks ? 1 : 0;
     if (tab[q].tail_slot >= 0) tab[q].tail_slot += nfull_slots;
@@ -2122,6 +2174,19 @@ static int batcher_submit_get(mec_batcher* b, Slot& s, std::vector<BatchReq*>& r
   if ((rc = s.dig.ensure(static_cast<size_t>(nslots * (k + r) * 32)))) return rc;
   if ((rc = s.flags.ensure(static_cast<size_t>(nslots * k)))) return rc;
   if ((rc = s.hflags.ensure(static_cast<size_t>(nslots * k)))) return rc;
+  // writeDataBlocks: 0 = the scatter kernel assembles every object in device memory and ONE copy per request takes it to the caller
+  // (fewest driver-side copy descriptors), 1 = the scatter kernel stores straight into the callers' buffers over PCIe, 2 = the copy
+  // engine moves every (request, shard, block) piece itself — measured in profiles/r2_concurrency.md
+  static const int out_mode = getenv("MEC_BATCHER_GET_OUT") ? atoi(getenv("MEC_BATCHER_GET_OUT")) : 0;
+  std::vector<int64_t> asm_off(reqs.size(), 0);
+  if (out_mode == 0) {
+    int64_t total = 0;
+    for (size_t q = 0; q < reqs.size(); q++) { asm_off[q] = total; total += round_up(tab[q].length, 256); }
+    if ((rc = s.src.ensure(static_cast<size_t>(total + 256)))) return rc;
+    for (size_t q = 0; q < reqs.size(); q++) tab[q].dst = static_cast<uint8_t*>(s.src.p) + asm_off[q];
+  }
+  const int phase_slot = static_cast<int>(&s - c->slots);
+  if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][0], s.st);
   MEC_CUDA_OK(cudaMemcpyAsync(s.dreq.p, tab, reqs.size() * sizeof(BatchGetDesc), cudaMemcpyHostToDevice, s.st));
   BatchGetParams gp;
   memset(&gp, 0, sizeof(gp));
@@ -2136,23 +2201,35 @@ static int batcher_submit_get(mec_batcher* b, Slot& s, std::vector<BatchReq*>& r
   // long ranges are staged by the copy engines (k strided copies per request are cheap next to megabytes of frames); short ones by
   // the gather kernel (no per-request driver call at all)
   const int64_t fstride = 32 + S;
-  for (size_t q = 0; q < reqs.size(); q++) {
-    const BatchGetDesc& d = tab[q];
-    if (!d.dma) continue;
-    const int64_t nf = d.nblocks - (d.tail_slot >= 0 ? 1 : 0);
-    for (int t = 0; t < k; t++) {
-      const uint8_t* f = d.files[chosen[t]] + d.start_block * fstride;
-      uint8_t* a = gp.arena + t * stride;
-      if (nf > 0)
-        MEC_CUDA_OK(cudaMemcpy2DAsync(a + d.slot0 * P, static_cast<size_t>(P), f, static_cast<size_t>(fstride), static_cast<size_t>(fstride),
-                                      static_cast<size_t>(nf), cudaMemcpyHostToDevice, s.st));
-      if (d.tail_slot >= 0)
-        MEC_CUDA_OK(cudaMemcpyAsync(a + d.tail_slot * P, f + nf * fstride, static_cast<size_t>(32 + d.last_len), cudaMemcpyHostToDevice, s.st));
+  {
+    // one 1-D copy per (request, survivor, block) frame — the arena pads frames to a 16-byte pitch — all of them in ONE batched call
+    std::vector<void*> dsts, srcs;
+    std::vector<size_t> sizes;
+    for (size_t q = 0; q < reqs.size(); q++) {
+      const BatchGetDesc& d = tab[q];
+      if (!d.dma) continue;
+      const int64_t nf = d.nblocks - (d.tail_slot >= 0 ? 1 : 0);
+      for (int t = 0; t < k; t++) {
+        const uint8_t* f = d.files[chosen[t]] + d.start_block * fstride;
+        uint8_t* a = gp.arena + t * stride;
+        for (int64_t j = 0; j < nf; j++) {
+          dsts.push_back(a + (d.slot0 + j) * P); srcs.push_back(const_cast<uint8_t*>(f) + j * fstride); sizes.push_back(static_cast<size_t>(fstride));
+        }
+        if (d.tail_slot >= 0) {
+          dsts.push_back(a + d.tail_slot * P); srcs.push_back(const_cast<uint8_t*>(f) + nf * fstride); sizes.push_back(static_cast<size_t>(32 + d.last_len));
+        }
+      }
     }
+    if ((rc = copy_batch(dsts, srcs, sizes, s.st))) return rc;
   }
-  batch_get_gather_kernel<<<dim3(gx, static_cast<unsigned>(k), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(gp);
-  MEC_CUDA_OK(cudaGetLastError());
-  c->eng->count_launch();
+  bool any_gather = false;
+  for (size_t q = 0; q < reqs.size(); q++) any_gather |= !tab[q].dma;
+  if (any_gather) {
+    batch_get_gather_kernel<<<dim3(gx, static_cast<unsigned>(k), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(gp);
+    MEC_CUDA_OK(cudaGetLastError());
+    c->eng->count_launch();
+  }
+  if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][1], s.st);
   MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(nslots * k), s.st));
   auto launch = [&](int64_t slot0, int64_t cnt, int64_t shard_len) -> int {
     FusedDesc d;
@@ -2172,9 +2249,47 @@ static int batcher_submit_get(mec_batcher* b, Slot& s, std::vector<BatchReq*>& r
   for (size_t q = 0; q < reqs.size(); q++)
     if (tab[q].tail_slot >= 0 && (rc = launch(tab[q].tail_slot, 1, tab[q].last_len))) return rc;
   MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(nslots * k), cudaMemcpyDeviceToHost, s.st));
-  batch_get_scatter_kernel<<<dim3(gx, static_cast<unsigned>(k), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(gp);
-  MEC_CUDA_OK(cudaGetLastError());
-  c->eng->count_launch();
+  if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][2], s.st);
+  if (out_mode == 2) {
+    // writeDataBlocks by the copy engine: one 1-D copy per (request, data shard, block) piece, all in one batched call
+    std::vector<void*> dsts, srcs;
+    std::vector<size_t> sizes;
+    int tpos[kMaxShards], qpos[kMaxShards];
+    for (int i = 0; i < k; i++) { tpos[i] = qpos[i] = -1; }
+    for (int t = 0; t < k; t++) if (chosen[t] < k) tpos[chosen[t]] = t;
+    for (int q = 0; q < r; q++) qpos[targets[q]] = q;
+    for (size_t rq = 0; rq < reqs.size(); rq++) {
+      const BatchGetDesc& d = tab[rq];
+      const int64_t hi = d.offset + d.length;
+      for (int64_t bb = 0; bb < d.nblocks; bb++) {
+        const bool is_tail = d.tail_slot >= 0 && bb == d.nblocks - 1;
+        const int64_t cur = is_tail ? d.last_len : S, slot = is_tail ? d.tail_slot : d.slot0 + bb;
+        const int64_t B = d.start_block + bb, blo = B * bs, bhi = std::min(blo + bs, d.total);
+        for (int i = 0; i < k; i++) {
+          const int64_t slo = blo + static_cast<int64_t>(i) * cur, shi = std::min(slo + cur, bhi);
+          const int64_t a = std::max(slo, d.offset), e = std::min(shi, hi);
+          if (e <= a) continue;
+          const uint8_t* src = tpos[i] >= 0 ? gp.arena + tpos[i] * stride + slot * P + 32 : gp.rebuilt + (slot * r + qpos[i]) * pitch;
+          dsts.push_back(d.dst + (a - d.offset)); srcs.push_back(const_cast<uint8_t*>(src) + (a - slo)); sizes.push_back(static_cast<size_t>(e - a));
+        }
+      }
+    }
+    if ((rc = copy_batch(dsts, srcs, sizes, s.st))) return rc;
+  } else {
+    batch_get_scatter_kernel<<<dim3(gx, static_cast<unsigned>(k), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(gp);
+    MEC_CUDA_OK(cudaGetLastError());
+    c->eng->count_launch();
+    if (out_mode == 0) {
+      std::vector<void*> dsts, srcs;
+      std::vector<size_t> sizes;
+      for (size_t q = 0; q < reqs.size(); q++) {
+        if (tab[q].length <= 0) continue;
+        dsts.push_back(reqs[q]->dst); srcs.push_back(static_cast<uint8_t*>(s.src.p) + asm_off[q]); sizes.push_back(static_cast<size_t>(tab[q].length));
+      }
+      if ((rc = copy_batch(dsts, srcs, sizes, s.st))) return rc;
+    }
+  }
+  if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][3], s.st);
   c->st_blocks_read += nslots;
   c->st_shards_rebuilt += nslots * r;
   b->st_batches++;
@@ -2189,11 +2304,15 @@ static void batcher_main(mec_batcher* b) {
   cudaSetDevice(c->device);
   InflightBatch inflight[kSlots];
   int head = 0, tail = 0, nbusy = 0;
+  using clk = std::chrono::steady_clock;
+  auto us_since = [](clk::time_point t0) { return std::chrono::duration_cast<std::chrono::microseconds>(clk::now() - t0).count(); };
   for (;;) {
     std::vector<BatchReq*> reqs;
     {
       std::unique_lock<std::mutex> lk(b->mu);
+      const auto t_idle = clk::now();
       if (nbusy == 0) b->cv_work.wait(lk, [&] { return b->stop || !b->queue.empty(); });
+      b->us_idle += us_since(t_idle);
       if (b->stop && b->queue.empty() && nbusy == 0) return;
       if (!b->queue.empty() && nbusy < kSlots) {
         // gather: whatever is queued now; when nothing is in flight, give concurrent callers max_wait_us to join
@@ -2207,13 +2326,22 @@ static void batcher_main(mec_batcher* b) {
         if (nbusy == 0 && b->max_wait_us > 0 && blocks_queued() < b->max_blocks)
           b->cv_work.wait_for(lk, std::chrono::microseconds(b->max_wait_us), [&] { return b->stop || blocks_queued() >= b->max_blocks; });
         // a batch = the oldest request plus everything queued behind it of the same kind (and, for GETs, the same reader set)
+        // a shallow pipeline is filled with several smaller batches rather than one big one: the fused kernel takes ~0.6 ms however few
+        // blocks it is given (one warp walks one erasure block), so the copy of one batch has to overlap the kernel of another —
+        // otherwise a closed loop of callers falls into a convoy (all of them in one batch, the GPU idle while they wake up)
+        static const int depth = getenv("MEC_BATCHER_DEPTH") ? atoi(getenv("MEC_BATCHER_DEPTH")) : 4;
+        int64_t cap = b->max_blocks;
+        if (depth > 0 && nbusy < depth - 1) {
+          const int64_t q = blocks_queued();
+          if (q > 8) cap = std::min(cap, std::max<int64_t>(4, ceil_frac(q, depth - nbusy)));
+        }
         int64_t nb = 0;
         const BatchReq* lead = b->queue.front();
         for (auto it = b->queue.begin(); it != b->queue.end();) {
           BatchReq* r = *it;
           if (r->kind != lead->kind || (r->kind == 1 && r->alive_mask != lead->alive_mask)) { ++it; continue; }
           const int64_t rb = r->kind == 0 ? ceil_frac(r->len, c->block_size) : (r->length / c->block_size + 2);
-          if (!reqs.empty() && nb + rb > b->max_blocks) break;
+          if (!reqs.empty() && nb + rb > cap) break;
           reqs.push_back(r);
           it = b->queue.erase(it);
           nb += rb;
@@ -2223,6 +2351,7 @@ static void batcher_main(mec_batcher* b) {
     if (!reqs.empty()) {
       Slot& s = c->slots[head];
       int rc;
+      const auto t_submit = clk::now();
       {
         std::lock_guard<std::mutex> lk(c->mu);
         inflight[head].is_get = reqs.front()->kind == 1;
@@ -2235,8 +2364,10 @@ static void batcher_main(mec_batcher* b) {
           rc = batcher_submit(b, s, reqs, &inflight[head].needs_retire);
         }
       }
+      b->us_submit += us_since(t_submit);
       inflight[head].reqs = reqs;
       inflight[head].busy = true;
+      inflight[head].traced = b->trace && rc == MEC_OK && (inflight[head].is_get || !inflight[head].needs_retire);
       if (rc != MEC_OK) {  // drain what was enqueued before the failure, then fail the whole batch
         cudaStreamSynchronize(s.st);
         batcher_finish(b, inflight[head], rc);
@@ -2252,8 +2383,19 @@ static void batcher_main(mec_batcher* b) {
       if (more && nbusy < kSlots) continue;  // keep the slots full before waiting on the oldest batch
     }
     if (nbusy > 0) {
+      const auto t_sync = clk::now();
       const cudaError_t e = cudaStreamSynchronize(c->slots[tail].st);
+      b->us_sync += us_since(t_sync);
+      if (inflight[tail].traced && e == cudaSuccess) {
+        float a = 0, k2 = 0, sc = 0;
+        cudaEventElapsedTime(&a, b->ev_ph[tail][0], b->ev_ph[tail][1]);
+        cudaEventElapsedTime(&k2, b->ev_ph[tail][1], b->ev_ph[tail][2]);
+        cudaEventElapsedTime(&sc, b->ev_ph[tail][2], b->ev_ph[tail][3]);
+        b->us_stage += static_cast<int64_t>(a * 1000); b->us_kernel += static_cast<int64_t>(k2 * 1000); b->us_scatter += static_cast<int64_t>(sc * 1000);
+      }
+      const auto t_fin = clk::now();
       batcher_finish(b, inflight[tail], e == cudaSuccess ? MEC_OK : MEC_ERR_CUDA);
+      b->us_finish += us_since(t_fin);
       tail = (tail + 1) % kSlots;
       nbusy--;
     }
@@ -2277,6 +2419,50 @@ extern "C" int mec_batcher_new(int k, int m, int64_t block_size, int device, int
   b->codec = c;
   if (max_batch_blocks > 0) b->max_blocks = max_batch_blocks;
   if (max_wait_us >= 0) b->max_wait_us = max_wait_us;
+  {
+    // size every slot for a full batch up front: growing a buffer later means cudaFree + cudaMalloc, which stall the whole device
+    // (all six batches in flight) for tens of milliseconds — seen as p99 spikes of 150-450 ms before
+    std::lock_guard<std::mutex> lk(c->mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    const int64_t S = c->S(), pitch = round_up(S, 16), P = round_up(32 + S, 16), slots = b->max_blocks + 64;
+    for (Slot& s : c->slots) {
+      if (rc == MEC_OK) rc = s.src.ensure(static_cast<size_t>(slots * block_size));
+      if (rc == MEC_OK) rc = s.out.ensure(static_cast<size_t>(slots * std::max(m, 1) * pitch));
+      if (rc == MEC_OK) rc = s.dig.ensure(static_cast<size_t>(slots * c->n * 32));
+      if (rc == MEC_OK) rc = s.hdig.ensure(static_cast<size_t>(slots * c->n * 32));
+      if (rc == MEC_OK) rc = s.aux.ensure(static_cast<size_t>(k * round_up(slots * P + 512, 256)));
+      if (rc == MEC_OK) rc = s.flags.ensure(static_cast<size_t>(slots * k));
+      if (rc == MEC_OK) rc = s.hflags.ensure(static_cast<size_t>(slots * k));
+      if (rc == MEC_OK) rc = s.dreq.ensure(static_cast<size_t>(slots) * std::max(sizeof(BatchReqDesc), sizeof(BatchGetDesc)));
+      if (rc == MEC_OK) rc = s.hreq.ensure(static_cast<size_t>(slots) * std::max(sizeof(BatchReqDesc), sizeof(BatchGetDesc)));
+    }
+    cudaSetDevice(cur);
+  }
+  if (rc) { mec_codec_free(c); delete b; return rc; }
+  b->trace = getenv("MEC_BATCHER_TRACE") != nullptr;
+  if (b->trace) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    for (int i = 0; i < kSlots; i++)
+      for (int j = 0; j < 4; j++)
+        if (cudaEventCreate(&b->ev_ph[i][j]) != cudaSuccess) { cudaGetLastError(); b->trace = false; }
+    cudaSetDevice(cur);
+  }
+  if (const char* e = getenv("MEC_BATCHER_GATHER_PCT")) b->gather_pct = std::max(0, std::min(100, atoi(e)));
+  if (b->gather_pct > 0) {
+    int cur = 0;
+    cudaGetDevice(&cur);
+    cudaSetDevice(device);
+    bool ok = cudaStreamCreateWithFlags(&b->aux, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < kSlots; i++)
+      ok = cudaEventCreateWithFlags(&b->ev_table[i], cudaEventDisableTiming) == cudaSuccess &&
+           cudaEventCreateWithFlags(&b->ev_gather[i], cudaEventDisableTiming) == cudaSuccess;
+    cudaSetDevice(cur);
+    if (!ok) { cudaGetLastError(); b->gather_pct = 0; }
+  }
   b->worker = std::thread(batcher_main, b);
   *out = b;
   return MEC_OK;
@@ -2290,6 +2476,13 @@ extern "C" void mec_batcher_free(mec_batcher* b) {
   }
   b->cv_work.notify_all();
   if (b->worker.joinable()) b->worker.join();
+  for (int i = 0; i < kSlots; i++) {
+    if (b->ev_table[i]) cudaEventDestroy(b->ev_table[i]);
+    if (b->ev_gather[i]) cudaEventDestroy(b->ev_gather[i]);
+    for (int j = 0; j < 4; j++)
+      if (b->ev_ph[i][j]) cudaEventDestroy(b->ev_ph[i][j]);
+  }
+  if (b->aux) cudaStreamDestroy(b->aux);
   mec_codec_free(b->serial);
   mec_codec_free(b->codec);
   delete b;
@@ -2370,5 +2563,12 @@ extern "C" int64_t mec_batcher_stat(const mec_batcher* b, const char* name) {
   if (!strcmp(name, "blocks")) return b->st_blocks.load();
   if (!strcmp(name, "kernel_batches")) return b->st_kernel_batches.load();
   if (!strcmp(name, "launches")) return b->codec->eng ? b->codec->eng->launches() : 0;
+  if (!strcmp(name, "us_submit")) return b->us_submit.load();
+  if (!strcmp(name, "us_sync")) return b->us_sync.load();
+  if (!strcmp(name, "us_finish")) return b->us_finish.load();
+  if (!strcmp(name, "us_idle")) return b->us_idle.load();
+  if (!strcmp(name, "us_stage")) return b->us_stage.load();
+  if (!strcmp(name, "us_kernel")) return b->us_kernel.load();
+  if (!strcmp(name, "us_scatter")) return b->us_scatter.load();
   return -1;
 }

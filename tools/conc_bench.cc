@@ -138,6 +138,11 @@ int main(int argc, char** argv) {
   if (bat) printf(", \"batches\": %lld, \"blocks_per_batch\": %.1f, \"launches\": %lld", static_cast<long long>(mec_batcher_stat(bat, "batches")),
                   static_cast<double>(mec_batcher_stat(bat, "blocks")) / std::max<int64_t>(1, mec_batcher_stat(bat, "batches")),
                   static_cast<long long>(mec_batcher_stat(bat, "launches")));
+  if (bat && getenv("MEC_BATCHER_TRACE"))
+    printf(", \"worker_us\": {\"submit\": %lld, \"sync\": %lld, \"finish\": %lld, \"idle\": %lld}, \"stream_us\": {\"stage\": %lld, \"kernel\": %lld, \"scatter\": %lld}",
+           (long long)mec_batcher_stat(bat, "us_submit"), (long long)mec_batcher_stat(bat, "us_sync"), (long long)mec_batcher_stat(bat, "us_finish"),
+           (long long)mec_batcher_stat(bat, "us_idle"), (long long)mec_batcher_stat(bat, "us_stage"), (long long)mec_batcher_stat(bat, "us_kernel"),
+           (long long)mec_batcher_stat(bat, "us_scatter"));
   if (mode == "pool" || mode == "get") printf(", \"pool\": %d", P);
   printf("}\n");
   if (bat) mec_batcher_free(bat);
