@@ -133,6 +133,7 @@ extern "C" int mec_codec_new(int k, int m, int64_t block_size, int algo, int dev
   if (const char* e = getenv("MEC_USE_AUTO")) c->opt.use_auto = atoi(e);
   if (const char* e = getenv("MEC_JIT")) c->opt.jit = atoi(e);
   if (const char* e = getenv("MEC_NO_ROWS3D")) c->opt.no_rows3d = atoi(e);
+  if (const char* e = getenv("MEC_SMALL_BLOCKS")) c->opt.small_blocks = atoll(e);
   if (const char* e = getenv("MEC_STATIC_GROUPS")) c->opt.static_groups = atoi(e);
   *out = c.release();
   return MEC_OK;
@@ -184,6 +185,7 @@ extern "C" int mec_set_option(mec_codec* c, const char* name, int64_t v) {
   else if (!strcmp(name, "no_rows3d")) c->opt.no_rows3d = static_cast<int>(v);
   else if (!strcmp(name, "chunk_blocks")) c->opt.chunk_blocks = v;
   else if (!strcmp(name, "static_groups")) c->opt.static_groups = static_cast<int>(v);
+  else if (!strcmp(name, "small_blocks")) c->opt.small_blocks = v;
   else if (!strcmp(name, "checksums")) c->checksums = static_cast<int>(v) & 7;
   else return MEC_ERR_INVALID_ARGUMENT;
   return MEC_OK;
@@ -199,6 +201,7 @@ extern "C" int64_t mec_get_stat(const mec_codec* c, const char* name) {
   if (!strcmp(name, "bytes_d2h")) return c->st_d2h;
   if (!strcmp(name, "jit_compiles")) return c->eng ? c->eng->jit_compiles() : 0;
   if (!strcmp(name, "jit_launches")) return c->eng ? c->eng->jit_launches() : 0;
+  if (!strcmp(name, "small_launches")) return c->eng ? c->eng->small_launches() : 0;
   if (!strcmp(name, "jit_ms")) return c->eng ? static_cast<int64_t>(c->eng->jit_seconds() * 1e3) : 0;
   if (!strcmp(name, "jit_disk_hits")) return c->eng ? c->eng->jit_disk_hits() : 0;
   return -1;
@@ -643,6 +646,22 @@ extern "C" int64_t mec_encode_sg(mec_codec* c, const uint8_t* src, int64_t len, 
   return encode_frames(c, src, len, files, false, data_digests, write_quorum, "mec_encode_sg");
 }
 
+// a train of independent copies as one driver call (CUDA 12.8 cudaMemcpyBatchAsync); MEC_NO_BATCH_COPY=1: one call per copy
+static int copy_batch(std::vector<void*>& dsts, std::vector<void*>& srcs, std::vector<size_t>& sizes, cudaStream_t st) {
+  if (dsts.empty()) return MEC_OK;
+  static const bool no_batch = getenv("MEC_NO_BATCH_COPY") != nullptr;
+  if (!no_batch && dsts.size() > 1) {
+    cudaMemcpyAttributes at = {};
+    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t idx0 = 0, fail = 0;
+    const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, st);
+    if (e == cudaSuccess) return MEC_OK;
+    cudaGetLastError();  // older driver: fall through to separate calls
+  }
+  for (size_t i = 0; i < dsts.size(); i++) MEC_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, st));
+  return MEC_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // reconstruct over frames (host)
 struct FrameGeom {
@@ -880,10 +899,11 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
     FrameGeom sub = g;  // geometry of the chunk: its last block is short only if it is the range's last block
     sub.nblocks = ch.nb;
     sub.last_len = (b0 + ch.nb == g.nblocks) ? g.last_len : g.S;
-    for (int t = 0; t < k; t++) {
+    // (measured: one contiguous copy per survivor file + a device-side move to the aligned pitch is slower than these 2-D copies,
+    //  36.4 vs 38.3 GiB/s on the 2 GiB GetObject, although a bare copy-engine probe favours contiguous transfers — tools/copy_probe.cu)
+    for (int t = 0; t < k; t++)
       if ((e = stage_frames(frames[ch.chosen[t]] + b0 * fstride, arena_ptr(s, stride, t), sub, s.st))) return e;
-      c->st_h2d += sub.file_bytes();
-    }
+    c->st_h2d += sub.file_bytes() * k;
     MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(ch.nb * k), s.st));
     if ((e = launch_reconstruct(c, g, ch, s, stride, rows_of[si].data(), pitch, hash_outputs))) return e;
     MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(ch.nb * k), cudaMemcpyDeviceToHost, s.st));
@@ -1942,22 +1962,6 @@ static void batcher_finish(mec_batcher* b, InflightBatch& fb, int rc) {
   }
   fb.reqs.clear();
   fb.busy = false;
-}
-
-// a train of independent copies as one driver call (CUDA 12.8 cudaMemcpyBatchAsync); MEC_NO_BATCH_COPY=1: one call per copy
-static int copy_batch(std::vector<void*>& dsts, std::vector<void*>& srcs, std::vector<size_t>& sizes, cudaStream_t st) {
-  if (dsts.empty()) return MEC_OK;
-  static const bool no_batch = getenv("MEC_NO_BATCH_COPY") != nullptr;
-  if (!no_batch && dsts.size() > 1) {
-    cudaMemcpyAttributes at = {};
-    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-    size_t idx0 = 0, fail = 0;
-    const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, st);
-    if (e == cudaSuccess) return MEC_OK;
-    cudaGetLastError();  // older driver: fall through to separate calls
-  }
-  for (size_t i = 0; i < dsts.size(); i++) MEC_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, st));
-  return MEC_OK;
 }
 
 // stage, launch and enqueue the copy-back of one merged batch on slot `s`

@@ -17,6 +17,7 @@
 #include <vector>
 #include "../../include/minio_ec.h"
 #include "ec_engine.h"
+#include "ec_small.cuh"
 #include "jit_headers.inc"
 
 namespace mec {
@@ -46,6 +47,7 @@ void DevBuf::release() {
 #define MEC_STATIC_CONFIGS(X) X(12, 4, 6) X(4, 2, 0) X(16, 4, 0) X(8, 8, 0) X(8, 4, 0) X(6, 2, 11) X(2, 2, 0)
 
 using KernelFn = void (*)(const FusedParams, const TmaMaps);
+using SmallFn = void (*)(const FusedParams);  // latency kernel (ec_small.cuh): one erasure block per CTA
 constexpr int kStaticEb = 4;  // erasure blocks per CTA of the compile-time specialised kernels
 
 struct StaticEntry {
@@ -58,6 +60,7 @@ struct StaticEntry {
   KernelFn aligned;   // TMA, S mod 16 == 0,    eb == kStaticEb
   KernelFn runtime;   // TMA, any alignment (per-row table), runtime eb
   KernelFn bytewise;  // byte-wise loader, runtime eb
+  SmallFn small;      // latency kernel for launches that cannot fill the GPU
 };
 static const StaticEntry kStaticTable[] = {
 #define X(K, M, A)                                                                                      \
@@ -68,7 +71,8 @@ static const StaticEntry kStaticTable[] = {
    (K + M == 16) ? fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, (K + M == 16) ? 1 : 0> : nullptr,          \
    fused_rs_hh_kernel<GfStatic<K, M>, true, A, kStaticEb, 0>,                                        \
    fused_rs_hh_kernel<GfStatic<K, M>, true, 0, kStaticEb, 0>,                                        \
-   fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0, 0>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0, 0>},
+   fused_rs_hh_kernel<GfStatic<K, M>, true, kAlignRuntime, 0, 0>, fused_rs_hh_kernel<GfStatic<K, M>, false, 0, 0, 0>, \
+   small_rs_hh_kernel<GfStatic<K, M>, small_gf_warps(K + M)>},
     MEC_STATIC_CONFIGS(X)
 #undef X
 };
@@ -79,6 +83,8 @@ static const KernelFn kDynAligned[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, 0
 static const KernelFn kDynRuntime[3] = {fused_rs_hh_kernel<GfDynamic<1>, true, kAlignRuntime, 0, 0>,
                                         fused_rs_hh_kernel<GfDynamic<2>, true, kAlignRuntime, 0, 0>,
                                         fused_rs_hh_kernel<GfDynamic<4>, true, kAlignRuntime, 0, 0>};
+static const SmallFn kDynSmall[2][3] = {{small_rs_hh_kernel<GfDynamic<1>, 3>, small_rs_hh_kernel<GfDynamic<2>, 3>, small_rs_hh_kernel<GfDynamic<4>, 3>},
+                                        {small_rs_hh_kernel<GfDynamic<1>, 4>, small_rs_hh_kernel<GfDynamic<2>, 4>, small_rs_hh_kernel<GfDynamic<4>, 4>}};
 static const KernelFn kDynBytewise[3] = {fused_rs_hh_kernel<GfDynamic<1>, false, 0, 0, 0>, fused_rs_hh_kernel<GfDynamic<2>, false, 0, 0, 0>,
                                          fused_rs_hh_kernel<GfDynamic<4>, false, 0, 0, 0>};
 
@@ -542,6 +548,41 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
         const uint8_t c = d.coef[static_cast<size_t>(j) * d.k + t];
         p.coef[j][t] = c;
       }
+  }
+
+  // ---- launches that cannot fill the GPU take the latency kernel: one erasure block per CTA, hash warps decoupled from the GF
+  // warps (ec_small.cuh).  The throughput kernel needs ~0.6 ms for a 1 MiB block however few there are (one warp walks it);
+  // this one ~0.15 ms, until about four blocks per SM — from there on both are bound by the same instruction count.
+  {
+    const int64_t small_max = opt.small_blocks >= 0 ? opt.small_blocks : 4ll * num_sms_;
+    if (d.nblocks <= small_max && d.S > 0 && opt.eb <= 0 && !opt.force_bytewise && opt.jit != 1 && d.nblocks < (1ll << 31) &&
+        (d.contiguous || d.in_ptr[0] != nullptr)) {
+      for (int t = 0; t < d.k; t++) p.in_ptr[t] = d.contiguous ? d.in_base + static_cast<int64_t>(t) * d.S : d.in_ptr[t];
+      p.in_block_stride = d.in_block_stride;
+      p.in_limit = d.contiguous ? d.in_block_len : d.S;
+      p.in_shard_step = d.contiguous ? d.S : 0;
+      const int gw = small_gf_warps(n);
+      const SmallFn sfn = se ? se->small : kDynSmall[gw - 3][d.r <= 1 ? 0 : (d.r == 2 ? 1 : 2)];
+      const void* kfn = reinterpret_cast<const void*>(sfn);
+      const size_t smem = small_smem_bytes(d.k, d.r, se == nullptr, gw);
+      const int threads = 32 * small_hash_warps(n) + 32 * gw;
+      if (smem <= 227 * 1024 && threads <= 256) {
+        bool hit = false;
+        for (const LaunchMemo& lm : launch_memo_)
+          if (lm.fn == kfn && lm.threads == threads && lm.smem == smem) { hit = true; break; }
+        if (!hit) {
+          MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+          if (launch_memo_.size() >= 64) launch_memo_.clear();
+          launch_memo_.push_back(LaunchMemo{kfn, threads, smem, 0});
+        }
+        void* args[] = {&p};
+        MEC_CUDA_OK(cudaLaunchKernel(kfn, dim3(static_cast<unsigned>(d.nblocks)), dim3(static_cast<unsigned>(threads)), args, smem, st));
+        MEC_CUDA_OK(cudaGetLastError());
+        launches_++;
+        small_launches_++;
+        return MEC_OK;
+      }
+    }
   }
 
   // ---- input addressing + loader choice.  TMA boxes must start on 16-byte boundaries, so each row is

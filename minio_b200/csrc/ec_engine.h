@@ -57,6 +57,7 @@ struct EngineOptions {
   int no_rows3d = 0;       // 1: never use the one-request-per-tile 3-D TMA fetch
   int use_auto = 0;        // 1: warp-autonomous pipeline (no CTA barriers) when k + r == 16; measured slower, off by default
   int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
+  int64_t small_blocks = -1; // launches of at most this many erasure blocks take the latency kernel (ec_small.cuh); -1: 4 per SM, 0: never
   int static_groups = 1;   // 1 (default): erasure-block groups are dealt to CTAs statically (g += gridDim.x); 0: through a claim counter —
                            // measured equal on a dedicated GPU (profiles/r2_kernel_ab.md), useful when SMs are shared or uneven
 };
@@ -71,6 +72,7 @@ class Engine {
   int64_t launches() const { return launches_; }
   void count_launch() { launches_++; }
   int64_t jit_compiles() const;  // process-wide
+  int64_t small_launches() const { return small_launches_; }  // launches that took the latency kernel (ec_small.cuh)
   int64_t jit_launches() const { return jit_launches_; }  // launches of this engine that ran a specialised kernel
   double jit_seconds() const;
   int64_t jit_disk_hits() const;  // specialised kernels loaded from the on-disk cache instead of compiled (process-wide)
@@ -86,6 +88,7 @@ class Engine {
   void* encode_tiled_ = nullptr;  // cuTensorMapEncodeTiled
   int64_t launches_ = 0;
   int64_t jit_launches_ = 0;
+  int64_t small_launches_ = 0;
   struct LaunchMemo { const void* fn; int threads; size_t smem; int per_sm; };
   std::vector<LaunchMemo> launch_memo_;
   uint32_t* claim_slots_ = nullptr;  // ring of per-launch group-claim counters (device)

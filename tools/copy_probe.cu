@@ -54,5 +54,50 @@ int main() {
              mode == 0 ? "h2d" : mode == 1 ? "h2d+d2h/3" : mode == 2 ? "h2d 2 streams" : mode == 3 ? "batch40" : "batch40+d2h/3", best / 1e9, best_issue);
     }
   }
+  // the GetObject staging pattern: rows of 32 + S bytes (a bitrot frame) from k part files into an arena with a 16-byte-aligned row pitch,
+  // and rows of S bytes back out into the object at pitch block_size: one 2-D copy per file vs one batched call of 1-D rows
+  {
+    const size_t S = 87382, F = 32 + S, P = (F + 15) / 16 * 16, rows = 256, k = 12, bs = 1 << 20;
+    for (int mode = 0; mode < 6; mode++) {  // 4: 2-D H2D + ONE contiguous D2H of the same bytes, 5: contiguous both ways; 0: 2-D H2D, 1: batched rows H2D, 2: 2-D both directions, 3: batched rows both directions
+      double best = 0;
+      for (int rep = 0; rep < 3; rep++) {
+        cudaDeviceSynchronize();
+        auto t0 = std::chrono::steady_clock::now();
+        for (int it = 0; it < 4; it++) {
+          if (mode == 4 || mode == 5) {
+            if (mode == 4) for (size_t t = 0; t < k; t++) cudaMemcpy2DAsync(d + t * rows * P, P, h + t * rows * F, F, F, rows, cudaMemcpyHostToDevice, s1);
+            else cudaMemcpyAsync(d, h, k * rows * F, cudaMemcpyHostToDevice, s1);
+            cudaMemcpyAsync(h2, d2, k * rows * S, cudaMemcpyDeviceToHost, s2);
+          } else if (mode == 0 || mode == 2) {
+            for (size_t t = 0; t < k; t++) cudaMemcpy2DAsync(d + t * rows * P, P, h + t * rows * F, F, F, rows, cudaMemcpyHostToDevice, s1);
+            if (mode == 2)
+              for (size_t t = 0; t < k; t++) cudaMemcpy2DAsync(h2 + t * S, bs, d2 + t * rows * P + 32, P, S, rows, cudaMemcpyDeviceToHost, s2);
+          } else {
+            std::vector<void*> dsts, srcs;
+            std::vector<size_t> sizes;
+            for (size_t t = 0; t < k; t++)
+              for (size_t r = 0; r < rows; r++) { dsts.push_back(d + (t * rows + r) * P); srcs.push_back(h + (t * rows + r) * F); sizes.push_back(F); }
+            cudaMemcpyAttributes at = {};
+            at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+            size_t idx0 = 0, fail = 0;
+            cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, s1);
+            if (mode == 3) {
+              dsts.clear(); srcs.clear(); sizes.clear();
+              for (size_t t = 0; t < k; t++)
+                for (size_t r = 0; r < rows; r++) { dsts.push_back(h2 + r * bs + t * S); srcs.push_back(d2 + (t * rows + r) * P + 32); sizes.push_back(S); }
+              cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, s2);
+            }
+          }
+        }
+        cudaStreamSynchronize(s1);
+        cudaStreamSynchronize(s2);
+        const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        const double gb = 4.0 * k * rows * F / sec / 1e9;
+        if (gb > best) best = gb;
+      }
+      printf("{\"pattern\": \"getobject rows\", \"mode\": \"%s\", \"h2d_GBps\": %.1f}\n",
+             mode == 0 ? "2-D h2d" : mode == 1 ? "batched rows h2d" : mode == 2 ? "2-D h2d + 2-D d2h" : mode == 3 ? "batched rows both ways" : mode == 4 ? "2-D h2d + contiguous d2h" : "contiguous both ways", best);
+    }
+  }
   return 0;
 }
