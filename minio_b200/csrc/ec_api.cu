@@ -539,6 +539,39 @@ extern "C" int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, 
   return MEC_OK;
 }
 
+// a train of independent copies as one driver call (CUDA 12.8 cudaMemcpyBatchAsync); MEC_NO_BATCH_COPY=1: one call per copy
+static int copy_batch(std::vector<void*>& dsts, std::vector<void*>& srcs, std::vector<size_t>& sizes, cudaStream_t st) {
+  if (dsts.empty()) return MEC_OK;
+  static const bool no_batch = getenv("MEC_NO_BATCH_COPY") != nullptr;
+  if (!no_batch && dsts.size() > 1) {
+    cudaMemcpyAttributes at = {};
+    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+    size_t idx0 = 0, fail = 0;
+    const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, st);
+    if (e == cudaSuccess) return MEC_OK;
+    cudaGetLastError();  // older driver: fall through to separate calls
+  }
+  for (size_t i = 0; i < dsts.size(); i++) MEC_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, st));
+  return MEC_OK;
+}
+
+struct CopyList {
+  std::vector<void*> dsts, srcs;
+  std::vector<size_t> sizes;
+  void add(void* d, const void* s, int64_t n) {
+    if (n <= 0) return;
+    dsts.push_back(d); srcs.push_back(const_cast<void*>(s)); sizes.push_back(static_cast<size_t>(n));
+  }
+  int flush(cudaStream_t st) {
+    const int rc = copy_batch(dsts, srcs, sizes, st);
+    dsts.clear(); srcs.clear(); sizes.clear();
+    return rc;
+  }
+};
+// chunks of at most this many erasure blocks move as ONE batched copy call per direction instead of one 2-D copy per shard:
+// a small GetObject is two driver calls instead of two dozen (the driver lock is what concurrent small requests queue on)
+constexpr int64_t kBatchedCopyBlocks = 8;
+
 // Frame sinks of Erasure.Encode.  files[i] is the part.N image of drive i: ([32 B digest][shard bytes])* with full frames
 // of 32 + S bytes and one short last frame.  Everything that is bulk moves by DMA straight from device memory into the
 // caller's frames (2-D copies: one row per erasure block); only the 32-byte digests go through a pinned staging buffer and
@@ -547,7 +580,7 @@ extern "C" int mec_encode_blocks(mec_codec* c, const uint8_t* src, int64_t len, 
 //   data drives:    with_data = true copies the data shards back from the staged object bytes (the device already holds
 //                   them); false leaves the data part to the caller (mec_encode_sg: the writer emits the digest followed
 //                   by the slice of its own source buffer, as streamingBitrotWriter.Write does — no copy anywhere)
-static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* files, bool with_data, uint8_t* data_digests) {
+static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* files, bool with_data, uint8_t* data_digests, CopyList* list = nullptr) {
   const int k = c->k, m = c->m;
   const int64_t bs = c->block_size, S = c->S(), fstride = 32 + S;
   cudaStream_t st = ch.st;
@@ -556,13 +589,18 @@ static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* file
     uint8_t* f = files[k + j];
     if (!f) continue;
     f += ch.b0 * fstride + 32;
-    if (ch.nfull > 0)
-      MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), ch.d_out + j * ch.pitch,
-                                    static_cast<size_t>(m * ch.pitch), static_cast<size_t>(S), static_cast<size_t>(ch.nfull),
-                                    cudaMemcpyDeviceToHost, st));
-    if (ch.tail > 0)
-      MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, ch.d_out_tail + j * ch.pitch,
-                                  static_cast<size_t>(per_t), cudaMemcpyDeviceToHost, st));
+    if (list) {
+      for (int64_t b = 0; b < ch.nfull; b++) list->add(f + b * fstride, ch.d_out + (b * m + j) * ch.pitch, S);
+      if (ch.tail > 0) list->add(f + ch.nfull * fstride, ch.d_out_tail + j * ch.pitch, per_t);
+    } else {
+      if (ch.nfull > 0)
+        MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), ch.d_out + j * ch.pitch,
+                                      static_cast<size_t>(m * ch.pitch), static_cast<size_t>(S), static_cast<size_t>(ch.nfull),
+                                      cudaMemcpyDeviceToHost, st));
+      if (ch.tail > 0)
+        MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, ch.d_out_tail + j * ch.pitch,
+                                    static_cast<size_t>(per_t), cudaMemcpyDeviceToHost, st));
+    }
     c->st_d2h += ch.nfull * S + per_t;
   }
   if (with_data) {
@@ -571,12 +609,16 @@ static int frames_enqueue(mec_codec* c, const EncChunk& ch, uint8_t* const* file
       if (!f) continue;
       f += ch.b0 * fstride + 32;
       const int64_t w = std::max<int64_t>(0, std::min(S, bs - static_cast<int64_t>(i) * S));  // Split: the last shard is short, the rest is zero padding
-      if (ch.nfull > 0 && w > 0)
+      if (list) {
+        for (int64_t b = 0; b < ch.nfull; b++) list->add(f + b * fstride, ch.d_src + b * bs + static_cast<int64_t>(i) * S, w);
+      } else if (ch.nfull > 0 && w > 0) {
         MEC_CUDA_OK(cudaMemcpy2DAsync(f, static_cast<size_t>(fstride), ch.d_src + static_cast<int64_t>(i) * S,
                                       static_cast<size_t>(bs), static_cast<size_t>(w), static_cast<size_t>(ch.nfull), cudaMemcpyDeviceToHost, st));
+      }
       if (ch.tail > 0) {
         const int64_t start = static_cast<int64_t>(i) * per_t, have = std::max<int64_t>(0, std::min(per_t, ch.tail - start));
-        if (have > 0)
+        if (list) list->add(f + ch.nfull * fstride, ch.d_src_tail + start, have);
+        else if (have > 0)
           MEC_CUDA_OK(cudaMemcpyAsync(f + ch.nfull * fstride, ch.d_src_tail + start,
                                       static_cast<size_t>(have), cudaMemcpyDeviceToHost, st));
       }
@@ -625,6 +667,12 @@ static int64_t encode_frames(mec_codec* c, const uint8_t* src, int64_t len, uint
   rc = encode_pipeline(
       c, src, len,
       [&](const EncChunk& ch) -> int {
+        if (ch.nb <= kBatchedCopyBlocks) {  // a small object: digests and every frame piece in ONE batched copy call
+          CopyList list;
+          list.add(ch.s->hdig.p, ch.s->dig.p, ch.nb * c->n * 32);
+          const int e = frames_enqueue(c, ch, files, with_data, data_digests, &list);
+          return e ? e : list.flush(ch.st);
+        }
         MEC_CUDA_OK(cudaMemcpyAsync(ch.s->hdig.p, ch.s->dig.p, static_cast<size_t>(ch.nb * c->n * 32), cudaMemcpyDeviceToHost, ch.st));
         return frames_enqueue(c, ch, files, with_data, data_digests);
       },
@@ -644,22 +692,6 @@ extern "C" int64_t mec_encode_sg(mec_codec* c, const uint8_t* src, int64_t len, 
                                  int write_quorum) {
   if (!data_digests) return MEC_ERR_INVALID_ARGUMENT;
   return encode_frames(c, src, len, files, false, data_digests, write_quorum, "mec_encode_sg");
-}
-
-// a train of independent copies as one driver call (CUDA 12.8 cudaMemcpyBatchAsync); MEC_NO_BATCH_COPY=1: one call per copy
-static int copy_batch(std::vector<void*>& dsts, std::vector<void*>& srcs, std::vector<size_t>& sizes, cudaStream_t st) {
-  if (dsts.empty()) return MEC_OK;
-  static const bool no_batch = getenv("MEC_NO_BATCH_COPY") != nullptr;
-  if (!no_batch && dsts.size() > 1) {
-    cudaMemcpyAttributes at = {};
-    at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
-    size_t idx0 = 0, fail = 0;
-    const cudaError_t e = cudaMemcpyBatchAsync(dsts.data(), srcs.data(), sizes.data(), dsts.size(), &at, &idx0, 1, &fail, st);
-    if (e == cudaSuccess) return MEC_OK;
-    cudaGetLastError();  // older driver: fall through to separate calls
-  }
-  for (size_t i = 0; i < dsts.size(); i++) MEC_CUDA_OK(cudaMemcpyAsync(dsts[i], srcs[i], sizes[i], cudaMemcpyDefault, st));
-  return MEC_OK;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -766,7 +798,8 @@ static int choose_readers(const mec_codec* c, const uint8_t* const* frames, cons
 
 // device->host copies of one verified-or-not chunk into the object sink (optimistic: a chunk that turns out to hold a corrupt
 // frame is redone from the bad block with other readers and its bytes are overwritten before the call returns)
-static int emit_object(mec_codec* c, const FrameGeom& g, const RangeSink& sk, const RChunk& ch, Slot& s, int64_t stride, int64_t pitch) {
+static int emit_object(mec_codec* c, const FrameGeom& g, const RangeSink& sk, const RChunk& ch, Slot& s, int64_t stride, int64_t pitch,
+                       CopyList* list = nullptr) {
   const int k = c->k, r = ch.r;
   const int64_t bs = sk.bs, S = g.S, P = g.dpitch();
   for (int i = 0; i < k; i++) {
@@ -785,8 +818,13 @@ static int emit_object(mec_codec* c, const FrameGeom& g, const RangeSink& sk, co
       const int64_t w = std::max<int64_t>(0, std::min(S, bs - static_cast<int64_t>(i) * S));
       if (w > 0) {
         const int64_t B = sk.first_block + ch.b0 + run0;
-        MEC_CUDA_OK(cudaMemcpy2DAsync(sk.dst + (B * bs + static_cast<int64_t>(i) * S - sk.lo), static_cast<size_t>(bs), base + run0 * spitch,
-                                      static_cast<size_t>(spitch), static_cast<size_t>(w), static_cast<size_t>(run1 - run0), cudaMemcpyDeviceToHost, s.st));
+        if (list) {
+          for (int64_t q = 0; q < run1 - run0; q++)
+            list->add(sk.dst + ((B + q) * bs + static_cast<int64_t>(i) * S - sk.lo), base + (run0 + q) * spitch, w);
+        } else {
+          MEC_CUDA_OK(cudaMemcpy2DAsync(sk.dst + (B * bs + static_cast<int64_t>(i) * S - sk.lo), static_cast<size_t>(bs), base + run0 * spitch,
+                                        static_cast<size_t>(spitch), static_cast<size_t>(w), static_cast<size_t>(run1 - run0), cudaMemcpyDeviceToHost, s.st));
+        }
         c->st_d2h += w * (run1 - run0);
       }
       run0 = -1;
@@ -803,13 +841,14 @@ static int emit_object(mec_codec* c, const FrameGeom& g, const RangeSink& sk, co
       const int64_t slo = blo + static_cast<int64_t>(i) * cur, shi = std::min(slo + cur, bhi);
       const int64_t a = std::max(slo, sk.lo), e = std::min(shi, sk.hi);
       if (e > a) {
-        MEC_CUDA_OK(cudaMemcpyAsync(sk.dst + (a - sk.lo), base + b * spitch + (a - slo), static_cast<size_t>(e - a), cudaMemcpyDeviceToHost, s.st));
+        if (list) list->add(sk.dst + (a - sk.lo), base + b * spitch + (a - slo), e - a);
+        else MEC_CUDA_OK(cudaMemcpyAsync(sk.dst + (a - sk.lo), base + b * spitch + (a - slo), static_cast<size_t>(e - a), cudaMemcpyDeviceToHost, s.st));
         c->st_d2h += e - a;
       }
     }
     if ((rc = flush(ch.nb))) return rc;
   }
-  return MEC_OK;
+  return list ? list->flush(s.st) : MEC_OK;
 }
 
 // rebuilt shards of a chunk -> frame-layout outputs (digest + shard per block)
@@ -901,13 +940,22 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
     sub.last_len = (b0 + ch.nb == g.nblocks) ? g.last_len : g.S;
     // (measured: one contiguous copy per survivor file + a device-side move to the aligned pitch is slower than these 2-D copies,
     //  36.4 vs 38.3 GiB/s on the 2 GiB GetObject, although a bare copy-engine probe favours contiguous transfers — tools/copy_probe.cu)
-    for (int t = 0; t < k; t++)
-      if ((e = stage_frames(frames[ch.chosen[t]] + b0 * fstride, arena_ptr(s, stride, t), sub, s.st))) return e;
+    const bool batched = ch.nb <= kBatchedCopyBlocks;
+    CopyList list;
+    if (batched) {
+      for (int t = 0; t < k; t++)
+        for (int64_t j = 0; j < ch.nb; j++)
+          list.add(arena_ptr(s, stride, t) + j * P, frames[ch.chosen[t]] + (b0 + j) * fstride, 32 + (j == ch.nb - 1 ? sub.last_len : g.S));
+      if ((e = list.flush(s.st))) return e;
+    } else {
+      for (int t = 0; t < k; t++)
+        if ((e = stage_frames(frames[ch.chosen[t]] + b0 * fstride, arena_ptr(s, stride, t), sub, s.st))) return e;
+    }
     c->st_h2d += sub.file_bytes() * k;
     MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(ch.nb * k), s.st));
     if ((e = launch_reconstruct(c, g, ch, s, stride, rows_of[si].data(), pitch, hash_outputs))) return e;
     MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(ch.nb * k), cudaMemcpyDeviceToHost, s.st));
-    if (sk.dst) { if ((e = emit_object(c, g, sk, ch, s, stride, pitch))) return e; }
+    if (sk.dst) { if ((e = emit_object(c, g, sk, ch, s, stride, pitch, batched ? &list : nullptr))) return e; }
     else if (sk.out) { if ((e = emit_frames(c, g, sk, ch, s, pitch))) return e; }
     return MEC_OK;
   };
