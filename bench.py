@@ -505,9 +505,10 @@ def heal_batch_leg(mb, local, nobj, barrier, max_over_ranks, world):
     enc.close()
     outs = [[pinned(fsz, local) if i in stale_set else None for i in range(n)] for _ in range(distinct)]
     stale = [i in stale_set for i in range(n)]
-    pool = [mb.Codec(k, m, bs, device=local) for _ in range(3)]
+    npool = int(os.environ.get("MEC_HEAL_POOL", "3"))
+    pool = [mb.Codec(k, m, bs, device=local) for _ in range(npool)]
     for c in pool:
-        c.set_option("jit", 1)
+        c.set_option("jit", int(os.environ.get("MEC_HEAL_JIT", "1")))
     objects = [(objs[o % distinct], stale, size) for o in range(nobj)]
     outs_all = [outs[o % distinct] for o in range(nobj)]
     mb.heal_batch(pool, objects[:6], outs_all[:6])   # warm: buffers, specialised kernel
@@ -523,7 +524,7 @@ def heal_batch_leg(mb, local, nobj, barrier, max_over_ranks, world):
             if a is not None:
                 mb.lib().mec_free_pinned(a.ctypes.data)
     mb.lib().mec_free_pinned(data.ctypes.data)
-    return {"name": f"4-host: RS(16,4) heal batch, {nobj} objects x 64 MiB per GPU through mec_heal_batch (pool of 3 handles, pinned NUMA-local part files)",
+    return {"name": f"4-host: RS(16,4) heal batch, {nobj} objects x 64 MiB per GPU through mec_heal_batch (pool of {npool} handles, pinned NUMA-local part files)",
             "value": world * nobj * size / GiB / dt, "unit": "GiB/s of object data healed", "seconds": dt, "objects_per_gpu": nobj,
             "h2d_bytes": nobj * k * fsz, "d2h_bytes": nobj * len(stale_set) * fsz, "bit_exact_vs_encode": bool(ok)}
 

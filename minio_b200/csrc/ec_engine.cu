@@ -552,9 +552,10 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
 
   // ---- launches that cannot fill the GPU take the latency kernel: one erasure block per CTA, hash warps decoupled from the GF
   // warps (ec_small.cuh).  The throughput kernel needs ~0.6 ms for a 1 MiB block however few there are (one warp walks it);
-  // this one ~0.15 ms, until about four blocks per SM — from there on both are bound by the same instruction count.
+  // this one ~0.17 ms up to one block per SM and still less at five per SM (0.45 vs 0.6 ms); beyond ~six per SM both are bound by the
+  // same instruction count and the throughput kernel's occupancy wins (profiles/r2_small_latency.md).
   {
-    const int64_t small_max = opt.small_blocks >= 0 ? opt.small_blocks : 4ll * num_sms_;
+    const int64_t small_max = opt.small_blocks >= 0 ? opt.small_blocks : 5ll * num_sms_;
     if (d.nblocks <= small_max && d.S > 0 && opt.eb <= 0 && !opt.force_bytewise && opt.jit != 1 && d.nblocks < (1ll << 31) &&
         (d.contiguous || d.in_ptr[0] != nullptr)) {
       for (int t = 0; t < d.k; t++) p.in_ptr[t] = d.contiguous ? d.in_base + static_cast<int64_t>(t) * d.S : d.in_ptr[t];

@@ -57,7 +57,7 @@ struct EngineOptions {
   int no_rows3d = 0;       // 1: never use the one-request-per-tile 3-D TMA fetch
   int use_auto = 0;        // 1: warp-autonomous pipeline (no CTA barriers) when k + r == 16; measured slower, off by default
   int64_t chunk_blocks = 0; // host pipeline chunk (0 = auto)
-  int64_t small_blocks = -1; // launches of at most this many erasure blocks take the latency kernel (ec_small.cuh); -1: 4 per SM, 0: never
+  int64_t small_blocks = -1; // launches of at most this many erasure blocks take the latency kernel (ec_small.cuh); -1: 5 per SM, 0: never
   int static_groups = 1;   // 1 (default): erasure-block groups are dealt to CTAs statically (g += gridDim.x); 0: through a claim counter —
                            // measured equal on a dedicated GPU (profiles/r2_kernel_ab.md), useful when SMs are shared or uneven
 };
