@@ -408,6 +408,7 @@ def main():
         configs["4-kernel: RS(16,4) heal of shards {0,7,16,19}, device-resident slice"] = dict(agg(r), generic_kernel_GiB_per_s=r["generic_GiB_per_s"])
         hb = heal_batch_leg(mb, local, args.heal_objects, barrier, max_over_ranks, world)
         configs[hb.pop("name")] = hb
+        configs["small: one 1 MiB RS(12,4) PutObject / degraded GetObject per call (the shape of cmd/erasure-encode.go:76-108; latency, not throughput)"] = small_request_leg(mb, local)
         sw = bc.sha256_sweep(8, 8, [64 << 10, 256 << 10, 1 << 20, 4 << 20], 1 << 30, quiet=True)
         configs["5: RS(8,8) encode + SHA256 whole-file bitrot, block-size sweep (1 GiB per point per GPU)"] = {
             f"{r['block_size'] >> 10} KiB": {"value": world * (1 << 30) / GiB / (max_over_ranks(r["ms"]) / 1e3), "unit": "GiB/s",
@@ -480,6 +481,61 @@ def main():
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def small_request_leg(mb, local):
+    """Launches that cannot fill the GPU: kernel time of a 1-block and a 148-block encode in the latency form (ec_small.cuh) and in the
+    throughput form, and the wall clock of one 1 MiB mec_encode_sg / mec_decode (four data drives offline) call from pinned buffers."""
+    import torch
+    k, m, bs = 12, 4, BS
+    L = mb.lib()
+    out = {"unit": "us"}
+    for nb in (1, 148):
+        src = torch.randint(0, 256, (nb * bs,), dtype=torch.uint8, device=f"cuda:{local}")
+        for name, small in (("latency_form", -1), ("throughput_form", 0)):
+            c = mb.Codec(k, m, bs, device=local)
+            c.set_option("small_blocks", small)
+            S = c.shard_size()
+            pitch = (S + 15) // 16 * 16
+            par = torch.zeros((nb * m * pitch,), dtype=torch.uint8, device=f"cuda:{local}")
+            dig = torch.zeros((nb * (k + m) * 32,), dtype=torch.uint8, device=f"cuda:{local}")
+            st = torch.cuda.current_stream()
+            ts = []
+            for it in range(15):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                c.encode_blocks_device(src.data_ptr(), nb * bs, par.data_ptr(), pitch, dig.data_ptr(), st.cuda_stream)
+                e1.record(st)
+                torch.cuda.synchronize()
+                if it >= 5:
+                    ts.append(e0.elapsed_time(e1) * 1e3)
+            out[f"kernel_{nb}_blocks_{name}"] = round(statistics.median(ts), 1)
+            c.close()
+    size = bs
+    c = mb.Codec(k, m, bs, device=local)
+    fsz = c.bitrot_file_size(size)
+    h_src = pinned(size, local)
+    h_src[:] = np.random.default_rng(5).integers(0, 256, size, dtype=np.uint8)
+    files = [pinned(fsz, local) for _ in range(k + m)]
+    dd, dst = pinned(k * 32, local), pinned(size, local)
+    assert L.mec_encode(c.h, h_src.ctypes.data, size, ptr_array(files), 0) == size
+    gptrs = ptr_array([None if i < 4 else files[i] for i in range(k + m)])
+    hint = C.c_int(0)
+    calls = {"call_put_1MiB_mec_encode_sg": lambda: L.mec_encode_sg(c.h, h_src.ctypes.data, size, ptr_array(files), dd.ctypes.data, 0),
+             "call_degraded_get_1MiB_mec_decode": lambda: L.mec_decode(c.h, gptrs, 0, size, size, dst.ctypes.data, C.byref(hint))}
+    for name, fn in calls.items():
+        ts = []
+        for it in range(60):
+            t0 = time.perf_counter()
+            assert fn() == size
+            if it >= 10:
+                ts.append((time.perf_counter() - t0) * 1e6)
+        out[name] = round(statistics.median(ts), 1)
+    out["bit_exact_roundtrip"] = bool(np.array_equal(dst, h_src))
+    c.close()
+    for a in files + [h_src, dd, dst]:
+        L.mec_free_pinned(a.ctypes.data)
+    return out
 
 
 def heal_batch_leg(mb, local, nobj, barrier, max_over_ranks, world):
