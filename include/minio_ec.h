@@ -270,10 +270,13 @@ int mec_selftest(int device);
  *      arrive before it is ready run the generic runtime-matrix kernel — no request ever waits for the compiler;
  *    1 compile (or wait for the background compile) inside the call — tests and benchmarks;  0 never specialise.
  * Compiled kernels are also kept on disk (MEC_JIT_CACHE_DIR, default $HOME/.cache/minio_b200, "off" disables), keyed by the kernel
- * sources, options and matrix: a restarted process loads the kernel of a pattern it has met before instead of recompiling. */
+ * sources, options and matrix: a restarted process loads the kernel of a pattern it has met before instead of recompiling.
+ * "small_blocks": launches of at most this many erasure blocks run the latency form of the kernel (one CTA per block, hash warps
+ *   decoupled from the GF warps: ~0.17 ms for a 1 MiB block instead of ~0.54 ms); -1 (default) = five per SM, 0 = never. */
 int mec_set_option(mec_codec* c, const char* name, int64_t value);
 /* Boundary counters (SURVEY §5 metrics row): name is one of "launches", "blocks_encoded", "blocks_read",
- * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms", "jit_disk_hits" (process-wide), "jit_launches".  -1 for unknown names.
+ * "shards_rebuilt", "corrupt_shards", "bytes_h2d", "bytes_d2h", "jit_compiles", "jit_ms", "jit_disk_hits" (process-wide), "jit_launches",
+ * "small_launches" (launches that took the latency form).  -1 for unknown names.
  * Every ABI call is also wrapped in an NVTX range (visible in Nsight Systems) — the tracing hook of SURVEY §5. */
 int64_t mec_get_stat(const mec_codec* c, const char* name);
 /* Stops background kernel specialisation and waits for a compile in flight.  Call before the process exits (exit()
