@@ -852,7 +852,7 @@ static int emit_object(mec_codec* c, const FrameGeom& g, const RangeSink& sk, co
 }
 
 // rebuilt shards of a chunk -> frame-layout outputs (digest + shard per block)
-static int emit_frames(mec_codec* c, const FrameGeom& g, const RangeSink& sk, const RChunk& ch, Slot& s, int64_t pitch) {
+static int emit_frames(mec_codec* c, const FrameGeom& g, const RangeSink& sk, const RChunk& ch, Slot& s, int64_t pitch, CopyList* list = nullptr) {
   const int k = c->k, r = ch.r;
   const int64_t fstride = 32 + g.S;
   const bool has_short = (ch.b0 + ch.nb == g.nblocks) && g.last_len != g.S;
@@ -861,6 +861,14 @@ static int emit_frames(mec_codec* c, const FrameGeom& g, const RangeSink& sk, co
     uint8_t* dst = sk.out[ch.targets[q]];
     if (!dst) continue;
     dst += ch.b0 * fstride;
+    if (list) {
+      for (int64_t b = 0; b < ch.nb; b++) {
+        list->add(dst + b * fstride, static_cast<uint8_t*>(s.dig.p) + (b * (k + r) + k + q) * 32, 32);
+        list->add(dst + b * fstride + 32, static_cast<uint8_t*>(s.out.p) + (b * r + q) * pitch, (has_short && b == nfull) ? g.last_len : g.S);
+      }
+      c->st_d2h += nfull * (32 + g.S) + (has_short ? 32 + g.last_len : 0);
+      continue;
+    }
     if (nfull > 0) {
       MEC_CUDA_OK(cudaMemcpy2DAsync(dst, static_cast<size_t>(fstride), static_cast<uint8_t*>(s.dig.p) + (k + q) * 32,
                                     static_cast<size_t>((k + r) * 32), 32, static_cast<size_t>(nfull), cudaMemcpyDeviceToHost, s.st));
@@ -875,7 +883,7 @@ static int emit_frames(mec_codec* c, const FrameGeom& g, const RangeSink& sk, co
     }
     c->st_d2h += nfull * (32 + g.S) + (has_short ? 32 + g.last_len : 0);
   }
-  return MEC_OK;
+  return list ? list->flush(s.st) : MEC_OK;
 }
 
 // Core of Decode / Heal: frames[i] point at the first frame of the range (host).  The range is cut into chunks that run through
@@ -956,7 +964,7 @@ static int reconstruct_range(mec_codec* c, const uint8_t* const* frames, const F
     if ((e = launch_reconstruct(c, g, ch, s, stride, rows_of[si].data(), pitch, hash_outputs))) return e;
     MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(ch.nb * k), cudaMemcpyDeviceToHost, s.st));
     if (sk.dst) { if ((e = emit_object(c, g, sk, ch, s, stride, pitch, batched ? &list : nullptr))) return e; }
-    else if (sk.out) { if ((e = emit_frames(c, g, sk, ch, s, pitch))) return e; }
+    else if (sk.out) { if ((e = emit_frames(c, g, sk, ch, s, pitch, batched ? &list : nullptr))) return e; }
     return MEC_OK;
   };
 
