@@ -2478,6 +2478,8 @@ extern "C" int mec_batcher_new(int k, int m, int64_t block_size, int device, int
   mec_batcher* b = new mec_batcher;
   b->codec = c;
   if (max_batch_blocks > 0) b->max_blocks = max_batch_blocks;
+  // a merged batch stages at most 1 GiB of object bytes: six slots are sized for a full batch up front (below)
+  b->max_blocks = std::max<int64_t>(1, std::min<int64_t>(b->max_blocks, (1ll << 30) / std::max<int64_t>(block_size, 1)));
   if (max_wait_us >= 0) b->max_wait_us = max_wait_us;
   {
     // size every slot for a full batch up front: growing a buffer later means cudaFree + cudaMalloc, which stall the whole device
@@ -2486,7 +2488,7 @@ extern "C" int mec_batcher_new(int k, int m, int64_t block_size, int device, int
     int cur = 0;
     cudaGetDevice(&cur);
     cudaSetDevice(device);
-    const int64_t S = c->S(), pitch = round_up(S, 16), P = round_up(32 + S, 16), slots = b->max_blocks + 64;
+    const int64_t S = c->S(), pitch = round_up(S, 16), P = round_up(32 + S, 16), slots = b->max_blocks + std::min<int64_t>(64, b->max_blocks / 8 + 4);
     for (Slot& s : c->slots) {
       if (rc == MEC_OK) rc = s.src.ensure(static_cast<size_t>(slots * block_size));
       if (rc == MEC_OK) rc = s.out.ensure(static_cast<size_t>(slots * std::max(m, 1) * pitch));
