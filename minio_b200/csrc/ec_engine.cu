@@ -495,6 +495,26 @@ static int make_map(void* fn, CUtensorMap* map, const void* base, uint64_t dim0,
   return MEC_OK;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is one number per kernel and device, shared by every handle of the process: the
+// runtime-matrix kernels are launched with footprints that depend on (k, r), so the limit is only ever raised (setting it for a
+// smaller launch would make the next larger one — possibly another handle's — fail with "invalid argument")
+int Engine::raise_smem_limit(const void* kfn, size_t smem) {
+  struct Entry { int device; const void* fn; size_t smem; };
+  static std::mutex mu;
+  static std::vector<Entry> limits;
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& e : limits)
+    if (e.device == device_ && e.fn == kfn) {
+      if (e.smem >= smem) return MEC_OK;
+      MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      e.smem = smem;
+      return MEC_OK;
+    }
+  MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  limits.push_back(Entry{device_, kfn, smem});
+  return MEC_OK;
+}
+
 int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStream_t st) {
   if (d.nblocks <= 0 || d.S < 0) return MEC_OK;
   if (d.S == 0 && (d.r > 0 || d.digests == nullptr)) return MEC_OK;  // S == 0: digest of the empty message only
@@ -568,14 +588,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       const size_t smem = small_smem_bytes(d.k, d.r, se == nullptr, gw);
       const int threads = 32 * small_hash_warps(n) + 32 * gw;
       if (smem <= 227 * 1024 && threads <= 256) {
-        bool hit = false;
-        for (const LaunchMemo& lm : launch_memo_)
-          if (lm.fn == kfn && lm.threads == threads && lm.smem == smem) { hit = true; break; }
-        if (!hit) {
-          MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-          if (launch_memo_.size() >= 64) launch_memo_.clear();
-          launch_memo_.push_back(LaunchMemo{kfn, threads, smem, 0});
-        }
+        int rc = raise_smem_limit(kfn, smem);
+        if (rc) return rc;
         void* args[] = {&p};
         MEC_CUDA_OK(cudaLaunchKernel(kfn, dim3(static_cast<unsigned>(d.nblocks)), dim3(static_cast<unsigned>(threads)), args, smem, st));
         MEC_CUDA_OK(cudaGetLastError());
@@ -749,7 +763,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     for (const LaunchMemo& lm : launch_memo_)
       if (lm.fn == kfn && lm.threads == threads && lm.smem == smem) { per_sm = lm.per_sm; hit = true; break; }
     if (!hit) {
-      MEC_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      int rc = raise_smem_limit(kfn, smem);
+      if (rc) return rc;
       MEC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, threads, smem));
       if (launch_memo_.size() >= 64) launch_memo_.clear();
       launch_memo_.push_back(LaunchMemo{kfn, threads, smem, per_sm});

@@ -91,6 +91,7 @@ class Engine {
   int64_t small_launches_ = 0;
   struct LaunchMemo { const void* fn; int threads; size_t smem; int per_sm; };
   std::vector<LaunchMemo> launch_memo_;
+  int raise_smem_limit(const void* kfn, size_t smem);
   uint32_t* claim_slots_ = nullptr;  // ring of per-launch group-claim counters (device)
   uint32_t claim_next_ = 0;
   // run-time specialised kernels, keyed by (k, r, matrix bytes)

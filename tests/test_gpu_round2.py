@@ -563,3 +563,22 @@ def test_bitrot_verify_batch_deep_scan(mb, oracle):
         assert c.bitrot_verify(bad[i], plens[i]) == want[i]
     assert c.bitrot_verify_batch([np.zeros(0, dtype=np.uint8)], [0]) == [0]
     c.close()
+
+
+def test_handles_of_different_width_share_the_runtime_matrix_kernels(mb, oracle):
+    """The runtime-matrix kernels (heal / degraded GET of small objects) are one function for every (k, r); their dynamic
+    shared-memory limit is a per-function attribute.  A narrow handle used between two calls of a wide one must not lower it."""
+    rng = np.random.default_rng(77)
+    wide, narrow = mb.Codec(12, 4, MiB), mb.Codec(4, 2, MiB)
+    dw, dn = rng.integers(0, 256, 3 * MiB + 11, dtype=np.uint8), rng.integers(0, 256, 2 * MiB + 5, dtype=np.uint8)
+    fw, fn = wide.encode(dw), narrow.encode(dn)
+    for _ in range(2):
+        for c, d, f, k in ((wide, dw, fw, 12), (narrow, dn, fn, 4), (wide, dw, fw, 12)):
+            n = len(f)
+            off = [None if i in (0, k) else f[i] for i in range(n)]
+            out, hint = c.decode(off, 0, d.size, d.size)
+            assert np.array_equal(out, d)
+            healed = c.heal(off, [i in (0, k) for i in range(n)], d.size)
+            assert np.array_equal(healed[0], f[0]) and np.array_equal(healed[k], f[k])
+    wide.close()
+    narrow.close()
