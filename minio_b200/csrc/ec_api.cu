@@ -1232,7 +1232,18 @@ static int verify_files_locked(mec_codec* c, int64_t nfiles, const uint8_t* cons
     if ((rc = s.hflags.ensure(static_cast<size_t>(chunk)))) return rc;
     MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(chunk), s.st));
     int64_t used = 0;
-    // fill the chunk with frames of consecutive files; full frames of all of them hash in ONE launch, short last frames one each
+    // fill the chunk with frames of consecutive files.  When the chunk is a launch the latency kernel takes (it is, unless options
+    // say otherwise: ~380 frames of a 1 MiB-block part file), every frame — full or short — hashes in ONE launch with a per-frame
+    // length table, and every frame is staged by ONE batched copy call: a scan over thousands of small part files costs two driver
+    // calls per 32 MiB, not two per file.  Otherwise: full frames in one launch, short last frames one launch each.
+    const bool one_launch = c->eng->small_ok(c->opt, chunk);
+    CopyList list;
+    int32_t* lens = nullptr;
+    if (one_launch) {
+      if ((rc = s.hreq.ensure(static_cast<size_t>(chunk) * sizeof(int32_t)))) return rc;
+      if ((rc = s.dreq.ensure(static_cast<size_t>(chunk) * sizeof(int32_t)))) return rc;
+      lens = static_cast<int32_t*>(s.hreq.p);
+    }
     struct Tail { int64_t slot, len; };
     std::vector<Tail> tails;
     while (f < nfiles && used < chunk) {
@@ -1240,7 +1251,13 @@ static int verify_files_locked(mec_codec* c, int64_t nfiles, const uint8_t* cons
       const int64_t nblocks = ceil_frac(part_lens[f], S), last_len = part_lens[f] - (nblocks - 1) * S;
       const int64_t take = std::min(chunk - used, nblocks - b0);
       FrameGeom sub{take, S, (b0 + take == nblocks) ? last_len : S};
-      if ((rc = stage_frames(files[f] + b0 * fstride, static_cast<uint8_t*>(s.src.p) + used * P, sub, s.st))) return rc;
+      if (one_launch) {  // every frame's length goes into the per-frame table; short runs of frames join the chunk's batched copy call
+        for (int64_t j = 0; j < take; j++) lens[used + j] = static_cast<int32_t>((j == take - 1) ? sub.last_len : S);
+      }
+      if (one_launch && take < kBatchedCopyBlocks) {
+        for (int64_t j = 0; j < take; j++)
+          list.add(static_cast<uint8_t*>(s.src.p) + (used + j) * P, files[f] + (b0 + j) * fstride, 32 + lens[used + j]);
+      } else if ((rc = stage_frames(files[f] + b0 * fstride, static_cast<uint8_t*>(s.src.p) + used * P, sub, s.st))) return rc;
       c->st_h2d += sub.file_bytes();
       if (sub.last_len != S) tails.push_back(Tail{used + take - 1, sub.last_len});
       inflight[si].push_back(Piece{f, take});
@@ -1249,9 +1266,11 @@ static int verify_files_locked(mec_codec* c, int64_t nfiles, const uint8_t* cons
       if (b0 == nblocks) { f++; b0 = 0; }
     }
     if (used == 0) break;
+    const int32_t* block_len = nullptr;
     auto launch = [&](int64_t slot0, int64_t cnt, int64_t len) -> int {
       FusedDesc d;
       d.k = 1; d.r = 0; d.contiguous = false; d.key = kMagicKey;
+      d.block_len = block_len;
       d.in_block_stride = P; d.expect_block_stride = P;
       const uint8_t* base = static_cast<const uint8_t*>(s.src.p) + slot0 * P;
       d.nblocks = cnt; d.S = static_cast<int32_t>(len);
@@ -1261,8 +1280,15 @@ static int verify_files_locked(mec_codec* c, int64_t nfiles, const uint8_t* cons
       d.corrupt = static_cast<uint8_t*>(s.flags.p) + slot0;
       return c->eng->launch_fused(d, c->opt, s.st);
     };
+    if (one_launch) {
+      if ((rc = list.flush(s.st))) return rc;
+      MEC_CUDA_OK(cudaMemcpyAsync(s.dreq.p, lens, static_cast<size_t>(used) * sizeof(int32_t), cudaMemcpyHostToDevice, s.st));
+      block_len = static_cast<const int32_t*>(s.dreq.p);
+      if ((rc = launch(0, used, S))) return rc;
+      tails.clear();
+    }
     // runs of full frames between the short ones (a short frame's digest covers fewer bytes: its own launch)
-    int64_t at = 0;
+    int64_t at = one_launch ? used : 0;
     for (size_t q = 0; q <= tails.size(); q++) {
       const int64_t end = q < tails.size() ? tails[q].slot : used;
       if (end > at && (rc = launch(at, end - at, S))) return rc;

@@ -575,13 +575,12 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   // this one ~0.17 ms up to one block per SM and still less at five per SM (0.45 vs 0.6 ms); beyond ~six per SM both are bound by the
   // same instruction count and the throughput kernel's occupancy wins (profiles/r2_small_latency.md).
   {
-    const int64_t small_max = opt.small_blocks >= 0 ? opt.small_blocks : 5ll * num_sms_;
-    if (d.nblocks <= small_max && d.S > 0 && opt.eb <= 0 && !opt.force_bytewise && opt.jit != 1 && d.nblocks < (1ll << 31) &&
-        (d.contiguous || d.in_ptr[0] != nullptr)) {
+    if (small_ok(opt, d.nblocks) && d.S > 0 && (d.contiguous || d.in_ptr[0] != nullptr)) {
       for (int t = 0; t < d.k; t++) p.in_ptr[t] = d.contiguous ? d.in_base + static_cast<int64_t>(t) * d.S : d.in_ptr[t];
       p.in_block_stride = d.in_block_stride;
       p.in_limit = d.contiguous ? d.in_block_len : d.S;
       p.in_shard_step = d.contiguous ? d.S : 0;
+      p.block_len = d.block_len;
       const int gw = small_gf_warps(n);
       const SmallFn sfn = se ? se->small : kDynSmall[gw - 3][d.r <= 1 ? 0 : (d.r == 2 ? 1 : 2)];
       const void* kfn = reinterpret_cast<const void*>(sfn);
@@ -599,6 +598,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       }
     }
   }
+
+  if (d.block_len != nullptr) return MEC_ERR_UNSUPPORTED;  // per-block lengths exist in the latency kernel only
 
   // ---- input addressing + loader choice.  TMA boxes must start on 16-byte boundaries, so each row is
   // fetched from the aligned-down address and the kernel skips in_align[t] bytes.

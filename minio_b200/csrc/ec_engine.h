@@ -45,6 +45,7 @@ struct FusedDesc {
   int64_t expect_block_stride = 0;
   uint8_t* corrupt = nullptr;
   const uint8_t* key = nullptr;    // 32-byte HighwayHash key (host)
+  const int32_t* block_len = nullptr;  // device: per-block shard bytes (<= S); only launches that take the latency kernel (see small_limit)
 };
 
 struct EngineOptions {
@@ -72,6 +73,10 @@ class Engine {
   int64_t launches() const { return launches_; }
   void count_launch() { launches_++; }
   int64_t jit_compiles() const;  // process-wide
+  int64_t small_limit(const EngineOptions& opt) const { return opt.small_blocks >= 0 ? opt.small_blocks : 5ll * num_sms_; }  // most blocks a latency-kernel launch takes
+  bool small_ok(const EngineOptions& opt, int64_t nblocks) const {  // would a launch of nblocks take the latency kernel?
+    return nblocks <= small_limit(opt) && opt.eb <= 0 && !opt.force_bytewise && opt.jit != 1 && nblocks < (1ll << 31);
+  }
   int64_t small_launches() const { return small_launches_; }  // launches that took the latency kernel (ec_small.cuh)
   int64_t jit_launches() const { return jit_launches_; }  // launches of this engine that ran a specialised kernel
   double jit_seconds() const;

@@ -69,6 +69,7 @@ struct FusedParams {
   int32_t nruns;                   // kLoadTmaRuns: input rows [run_row0[q], run_row0[q+1]) share tensor map q (x, block, row)
   uint8_t run_row0[kMaxRuns + 1];
   uint32_t* work_counter;          // optional: groups beyond the first of every CTA are claimed from this counter (zeroed per launch)
+  const int32_t* block_len;        // latency kernel only: shard bytes of every erasure block (nullptr: S for all) — frames of many files in one launch
 };
 
 // ------------------------------------------------------------------ GF policies

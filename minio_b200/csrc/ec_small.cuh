@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256, 2) small_rs_hh_kernel(const __grid_consta
   const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
 
   const int64_t b = blockIdx.x;
-  const int32_t S = p.S;
+  const int32_t S = p.block_len != nullptr ? p.block_len[b] : p.S;  // per-block lengths: the short last frames of many part files ride in one launch
   const int nst = (S + kSmallSuper - 1) / kSmallSuper;
 
   if (tid == 0) {

@@ -582,3 +582,34 @@ def test_handles_of_different_width_share_the_runtime_matrix_kernels(mb, oracle)
             assert np.array_equal(healed[0], f[0]) and np.array_equal(healed[k], f[k])
     wide.close()
     narrow.close()
+
+
+def test_deep_scan_over_many_small_part_files_is_one_launch_per_chunk(mb, oracle):
+    """A scan over hundreds of part files of one short frame each (small objects of odd sizes): every frame of a chunk is staged by one
+    batched copy call and hashed by ONE launch with a per-frame length table (latency kernel, FusedParams::block_len); verdicts equal the
+    oracle's, with and without that path."""
+    k, m, bs = 12, 4, MiB
+    c = mb.Codec(k, m, bs)
+    S = c.shard_size()
+    rng = np.random.default_rng(12)
+    files, plens = [], []
+    for o in range(24):
+        size = int(rng.integers(1, 2 * MiB + 500_000))   # 1 to 3 frames per part file, the last one short
+        fs = c.encode(rng.integers(0, 256, size, dtype=np.uint8))
+        files += fs
+        plens += [c.shard_file_size(size)] * len(fs)
+    want = [0] * len(files)
+    for i, pos in ((5, 3), (77, 40), (200, -1), (333, 31)):
+        files[i] = files[i].copy()
+        files[i][pos] ^= 0x20
+        want[i] = -7
+    for i in (5, 77, 200, 333):
+        assert oracle.bitrot_verify(oracle.HIGHWAYHASH256S, files[i], plens[i], S) == -7
+    l0 = c.launches
+    assert c.bitrot_verify_batch(files, plens) == want
+    one = c.launches - l0
+    c.set_option("small_blocks", 0)
+    l0 = c.launches
+    assert c.bitrot_verify_batch(files, plens) == want
+    assert one <= 3 and c.launches - l0 > 100, (one, c.launches - l0)
+    c.close()
