@@ -63,7 +63,8 @@ struct Slot {
   DevBuf src, out, dig, aux, flags;  // aux: survivor arena of a reconstruct chunk / shard files of the whole-file path
   DevBuf crc_part, crc_out;          // object checksums of an encode chunk (crc.cuh)
   DevBuf dreq;                       // request table of a merged batch (batch_copy.cuh)
-  PinBuf hdig, hflags, hcrc, hreq;
+  DevBuf blk;                        // per-block geometry of a merged launch (SmallBlock / per-frame lengths)
+  PinBuf hdig, hflags, hcrc, hreq, hblk;
   cudaStream_t st = nullptr;
 };
 
@@ -165,7 +166,7 @@ extern "C" void mec_codec_free(mec_codec* c) {
   for (auto& s : c->slots) {
     if (s.st) { cudaStreamSynchronize(s.st); cudaStreamDestroy(s.st); }
     s.src.release(); s.out.release(); s.dig.release(); s.aux.release(); s.flags.release();
-    s.hdig.release(); s.hflags.release(); s.hcrc.release(); s.crc_part.release(); s.crc_out.release(); s.dreq.release(); s.hreq.release();
+    s.hdig.release(); s.hflags.release(); s.hcrc.release(); s.crc_part.release(); s.crc_out.release(); s.dreq.release(); s.hreq.release(); s.blk.release(); s.hblk.release();
   }
   c->flags.release();
   c->crc_tables.release();
@@ -2148,10 +2149,34 @@ static int batcher_submit(mec_batcher* b, Slot& s, std::vector<BatchReq*>& reqs,
     }
     if (ndma > 0 && ndma < reqs.size()) MEC_CUDA_OK(cudaStreamWaitEvent(s.st, b->ev_gather[static_cast<int>(&s - c->slots)], 0));
     if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][1], s.st);
-    if (total_full > 0 && (rc = encode_device_locked(c, dsrc, total_full * bs, dout, pitch, ddig, s.st))) return rc;
-    for (BatchReq* r : reqs)
-      if (r->ch.tail > 0 && (rc = encode_device_locked(c, r->ch.d_src_tail, r->ch.tail, r->ch.d_out_tail, pitch, ddig + (r->ch.h_dig_tail - hdig), s.st)))
-        return rc;
+    if (c->eng->small_ok(c->opt, nslots)) {
+      // ONE launch for every block of the batch, full or short (objects smaller than a block are nothing but a short block): the
+      // latency kernel takes the geometry of each block from a table
+      if ((rc = s.hblk.ensure(static_cast<size_t>(nslots) * sizeof(SmallBlock)))) return rc;
+      if ((rc = s.blk.ensure(static_cast<size_t>(nslots) * sizeof(SmallBlock)))) return rc;
+      SmallBlock* bt = static_cast<SmallBlock*>(s.hblk.p);
+      for (int64_t q = 0; q < total_full; q++) bt[q] = SmallBlock{q * bs, static_cast<int32_t>(S), static_cast<int32_t>(bs)};
+      for (size_t q = 0; q < reqs.size(); q++)
+        if (tab[q].tail_slot >= 0) {
+          const int64_t tl = tab[q].len % bs;
+          bt[tab[q].tail_slot] = SmallBlock{tab[q].tail_src_off, static_cast<int32_t>(ceil_frac(tl, k)), static_cast<int32_t>(tl)};
+        }
+      MEC_CUDA_OK(cudaMemcpyAsync(s.blk.p, bt, static_cast<size_t>(nslots) * sizeof(SmallBlock), cudaMemcpyHostToDevice, s.st));
+      FusedDesc d;
+      d.k = k; d.r = m;
+      d.coef = c->matrix.data() + static_cast<size_t>(k) * k;
+      d.static_encode = true; d.contiguous = true; d.key = kMagicKey; d.out_pitch = pitch;
+      d.nblocks = nslots; d.S = static_cast<int32_t>(S);
+      d.in_base = dsrc; d.in_block_stride = bs; d.in_block_len = bs;
+      d.out = dout; d.digests = ddig;
+      d.blocks = static_cast<const SmallBlock*>(s.blk.p);
+      if ((rc = c->eng->launch_fused(d, c->opt, s.st))) return rc;
+    } else {
+      if (total_full > 0 && (rc = encode_device_locked(c, dsrc, total_full * bs, dout, pitch, ddig, s.st))) return rc;
+      for (BatchReq* r : reqs)
+        if (r->ch.tail > 0 && (rc = encode_device_locked(c, r->ch.d_src_tail, r->ch.tail, r->ch.d_out_tail, pitch, ddig + (r->ch.h_dig_tail - hdig), s.st)))
+          return rc;
+    }
     if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][2], s.st);
     batch_scatter_kernel<<<dim3(static_cast<unsigned>(std::min<int64_t>(max_nb, 16)), static_cast<unsigned>(n), static_cast<unsigned>(reqs.size())), 128, 0, s.st>>>(cp);
     MEC_CUDA_OK(cudaGetLastError());
@@ -2322,8 +2347,10 @@ static int batcher_submit_get(mec_batcher* b, Slot& s, std::vector<BatchReq*>& r
   }
   if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][1], s.st);
   MEC_CUDA_OK(cudaMemsetAsync(s.flags.p, 0, static_cast<size_t>(nslots * k), s.st));
+  const int32_t* block_len = nullptr;
   auto launch = [&](int64_t slot0, int64_t cnt, int64_t shard_len) -> int {
     FusedDesc d;
+    d.block_len = block_len;
     d.k = k; d.r = r; d.coef = rows.data(); d.static_encode = false; d.contiguous = false; d.hash_outputs = false;
     d.key = kMagicKey; d.out_pitch = pitch; d.expect_block_stride = P; d.in_block_stride = P;
     d.nblocks = cnt; d.S = static_cast<int32_t>(shard_len);
@@ -2336,9 +2363,22 @@ static int batcher_submit_get(mec_batcher* b, Slot& s, std::vector<BatchReq*>& r
     d.corrupt = static_cast<uint8_t*>(s.flags.p) + slot0 * k;
     return c->eng->launch_fused(d, c->opt, s.st);
   };
-  if (nfull_slots > 0 && (rc = launch(0, nfull_slots, S))) return rc;  // ONE launch for every caller's full blocks
-  for (size_t q = 0; q < reqs.size(); q++)
-    if (tab[q].tail_slot >= 0 && (rc = launch(tab[q].tail_slot, 1, tab[q].last_len))) return rc;
+  if (ntails > 0 && c->eng->small_ok(c->opt, nslots)) {
+    // ONE launch for every block of every caller, the short last ones included (per-block shard lengths in the latency kernel)
+    if ((rc = s.hblk.ensure(static_cast<size_t>(nslots) * sizeof(int32_t)))) return rc;
+    if ((rc = s.blk.ensure(static_cast<size_t>(nslots) * sizeof(int32_t)))) return rc;
+    int32_t* lens = static_cast<int32_t*>(s.hblk.p);
+    for (int64_t q = 0; q < nfull_slots; q++) lens[q] = static_cast<int32_t>(S);
+    for (size_t q = 0; q < reqs.size(); q++)
+      if (tab[q].tail_slot >= 0) lens[tab[q].tail_slot] = static_cast<int32_t>(tab[q].last_len);
+    MEC_CUDA_OK(cudaMemcpyAsync(s.blk.p, lens, static_cast<size_t>(nslots) * sizeof(int32_t), cudaMemcpyHostToDevice, s.st));
+    block_len = static_cast<const int32_t*>(s.blk.p);
+    if ((rc = launch(0, nslots, S))) return rc;
+  } else {
+    if (nfull_slots > 0 && (rc = launch(0, nfull_slots, S))) return rc;  // ONE launch for every caller's full blocks
+    for (size_t q = 0; q < reqs.size(); q++)
+      if (tab[q].tail_slot >= 0 && (rc = launch(tab[q].tail_slot, 1, tab[q].last_len))) return rc;
+  }
   MEC_CUDA_OK(cudaMemcpyAsync(s.hflags.p, s.flags.p, static_cast<size_t>(nslots * k), cudaMemcpyDeviceToHost, s.st));
   if (b->trace) cudaEventRecord(b->ev_ph[phase_slot][2], s.st);
   if (out_mode == 2) {

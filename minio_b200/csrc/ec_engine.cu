@@ -581,6 +581,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       p.in_limit = d.contiguous ? d.in_block_len : d.S;
       p.in_shard_step = d.contiguous ? d.S : 0;
       p.block_len = d.block_len;
+      p.blocks = d.blocks;
       const int gw = small_gf_warps(n);
       const SmallFn sfn = se ? se->small : kDynSmall[gw - 3][d.r <= 1 ? 0 : (d.r == 2 ? 1 : 2)];
       const void* kfn = reinterpret_cast<const void*>(sfn);
@@ -599,7 +600,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     }
   }
 
-  if (d.block_len != nullptr) return MEC_ERR_UNSUPPORTED;  // per-block lengths exist in the latency kernel only
+  if (d.block_len != nullptr || d.blocks != nullptr) return MEC_ERR_UNSUPPORTED;  // per-block geometry exists in the latency kernel only
 
   // ---- input addressing + loader choice.  TMA boxes must start on 16-byte boundaries, so each row is
   // fetched from the aligned-down address and the kernel skips in_align[t] bytes.

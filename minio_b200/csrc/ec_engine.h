@@ -45,7 +45,8 @@ struct FusedDesc {
   int64_t expect_block_stride = 0;
   uint8_t* corrupt = nullptr;
   const uint8_t* key = nullptr;    // 32-byte HighwayHash key (host)
-  const int32_t* block_len = nullptr;  // device: per-block shard bytes (<= S); only launches that take the latency kernel (see small_limit)
+  const int32_t* block_len = nullptr;  // device: per-block shard bytes (<= S); only launches that take the latency kernel (see small_ok)
+  const SmallBlock* blocks = nullptr;  // device, contiguous encode: per-block geometry relative to in_base; S = the largest shard length
 };
 
 struct EngineOptions {

@@ -45,6 +45,14 @@ struct alignas(64) TmaMaps {
   CUtensorMap m[kMaxMaps];
 };
 
+// latency kernel, contiguous encode: the geometry of every erasure block of a launch — blocks of different objects (full blocks and the
+// short last blocks of many PutObjects) ride in ONE launch
+struct SmallBlock {
+  int64_t in_off;   // bytes from FusedParams::in_ptr[0] to the block's first byte; row t starts S * t further on
+  int32_t S;        // shard bytes of this block = ceil(bytes / k)
+  int32_t bytes;    // object bytes in the block (Split pads the rest of k * S with zeros)
+};
+
 struct FusedParams {
   int k, r, eb, tma_mode;
   int tiles_3d;                    // ROWS3D: tiles [0, tiles_3d) of a shard are fetched with one 3-D request
@@ -70,6 +78,7 @@ struct FusedParams {
   uint8_t run_row0[kMaxRuns + 1];
   uint32_t* work_counter;          // optional: groups beyond the first of every CTA are claimed from this counter (zeroed per launch)
   const int32_t* block_len;        // latency kernel only: shard bytes of every erasure block (nullptr: S for all) — frames of many files in one launch
+  const SmallBlock* blocks;        // latency kernel only, contiguous encode: per-block offset / shard bytes / object bytes (nullptr: uniform)
 };
 
 // ------------------------------------------------------------------ GF policies

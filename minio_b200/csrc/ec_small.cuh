@@ -68,7 +68,8 @@ __global__ void __launch_bounds__(256, 2) small_rs_hh_kernel(const __grid_consta
   const int rpad = (r + kRChunk - 1) / kRChunk * kRChunk;
 
   const int64_t b = blockIdx.x;
-  const int32_t S = p.block_len != nullptr ? p.block_len[b] : p.S;  // per-block lengths: the short last frames of many part files ride in one launch
+  // per-block geometry: the short last frames of many part files, or the blocks of many PutObjects, ride in one launch
+  const int32_t S = p.blocks != nullptr ? p.blocks[b].S : (p.block_len != nullptr ? p.block_len[b] : p.S);
   const int nst = (S + kSmallSuper - 1) / kSmallSuper;
 
   if (tid == 0) {
@@ -81,6 +82,10 @@ __global__ void __launch_bounds__(256, 2) small_rs_hh_kernel(const __grid_consta
   if (tid < k) {
     const uint8_t* a = p.in_ptr[tid] + b * p.in_block_stride;
     int64_t valid = p.in_limit - static_cast<int64_t>(tid) * p.in_shard_step;
+    if (p.blocks != nullptr) {
+      a = p.in_ptr[0] + p.blocks[b].in_off + static_cast<int64_t>(tid) * S;
+      valid = static_cast<int64_t>(p.blocks[b].bytes) - static_cast<int64_t>(tid) * S;
+    }
     valid = valid < 0 ? 0 : (valid > S ? S : valid);
     SmallRow rw;
     rw.base16 = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(a) & ~static_cast<uintptr_t>(15));

@@ -34,7 +34,9 @@ int main(int argc, char** argv) {
   signal(SIGABRT, on_segv);
   std::string mode = argc > 1 ? argv[1] : "batcher";
   const int T = argc > 2 ? atoi(argv[2]) : 256;
-  const int64_t osize = (argc > 3 ? atoll(argv[3]) : 1) << 20;
+  // object size: MiB, or KiB with a 'k' suffix (objects smaller than one erasure block: "256k")
+  const std::string osz = argc > 3 ? argv[3] : "1";
+  const int64_t osize = (!osz.empty() && (osz.back() == 'k' || osz.back() == 'K')) ? atoll(osz.c_str()) << 10 : atoll(osz.c_str()) << 20;
   const int calls_per_thread = argc > 4 ? atoi(argv[4]) : 32;
   const int P = argc > 5 ? atoi(argv[5]) : 8;
   const int device = argc > 6 ? atoi(argv[6]) : 0;
@@ -131,9 +133,9 @@ int main(int argc, char** argv) {
   for (auto& v : lat) all.insert(all.end(), v.begin(), v.end());
   std::sort(all.begin(), all.end());
   const double total = static_cast<double>(T) * calls_per_thread * osize;
-  printf("{\"mode\": \"%s\", \"threads\": %d, \"object_MiB\": %lld, \"calls\": %zu, \"seconds\": %.4f, \"GiB_per_s\": %.2f, \"calls_per_s\": %.0f, "
+  printf("{\"mode\": \"%s\", \"threads\": %d, \"object_MiB\": %lld, \"object_bytes\": %lld, \"calls\": %zu, \"seconds\": %.4f, \"GiB_per_s\": %.2f, \"calls_per_s\": %.0f, "
          "\"p50_us\": %.0f, \"p99_us\": %.0f, \"errors\": %lld",
-         mode.c_str(), T, static_cast<long long>(osize >> 20), all.size(), sec, total / sec / (1 << 30), all.size() / sec, all[all.size() / 2],
+         mode.c_str(), T, static_cast<long long>(osize >> 20), static_cast<long long>(osize), all.size(), sec, total / sec / (1 << 30), all.size() / sec, all[all.size() / 2],
          all[static_cast<size_t>(all.size() * 0.99)], static_cast<long long>(errors.load()));
   if (bat) printf(", \"batches\": %lld, \"blocks_per_batch\": %.1f, \"launches\": %lld", static_cast<long long>(mec_batcher_stat(bat, "batches")),
                   static_cast<double>(mec_batcher_stat(bat, "blocks")) / std::max<int64_t>(1, mec_batcher_stat(bat, "batches")),
