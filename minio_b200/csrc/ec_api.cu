@@ -375,6 +375,14 @@ static int encode_device_locked(mec_codec* c, const uint8_t* d_src, int64_t len,
   d.contiguous = true;
   d.key = kMagicKey;
   d.out_pitch = pitch;
+  if (nfull > 0 && tail > 0 && c->eng->small_ok(c->opt, nfull + 1)) {
+    // a small object with a short last block: ONE launch of the latency kernel, the last block carries its own geometry
+    d.nblocks = nfull + 1; d.S = static_cast<int32_t>(S);
+    d.in_base = d_src; d.in_block_stride = bs; d.in_block_len = bs;
+    d.out = d_parity; d.digests = d_digests;
+    d.tail_block = nfull; d.tail_in_off = nfull * bs; d.tail_S = static_cast<int32_t>(ceil_frac(tail, c->k)); d.tail_bytes = static_cast<int32_t>(tail);
+    return c->eng->launch_fused(d, c->opt, st);
+  }
   if (nfull > 0) {
     d.nblocks = nfull; d.S = static_cast<int32_t>(S);
     d.in_base = d_src; d.in_block_stride = bs; d.in_block_len = bs;
@@ -755,6 +763,19 @@ static int launch_reconstruct(mec_codec* c, const FrameGeom& g, const RChunk& ch
   // the range's short last block (if this chunk holds it) is a second launch with its own shard length
   const bool has_short = (ch.b0 + ch.nb == g.nblocks) && g.last_len != g.S;
   const int64_t nfull = has_short ? ch.nb - 1 : ch.nb;
+  if (has_short && nfull > 0 && c->eng->small_ok(c->opt, ch.nb)) {  // one launch: the last block carries its own shard length
+    d.nblocks = ch.nb;
+    d.S = static_cast<int32_t>(g.S);
+    d.tail_block = nfull; d.tail_S = static_cast<int32_t>(g.last_len);
+    for (int t = 0; t < k; t++) {
+      const uint8_t* base = arena_ptr(s, stride, t);
+      d.map_base[t] = base; d.map_len[t] = stride; d.expect_ptr[t] = base; d.in_ptr[t] = base + 32;
+    }
+    d.out = static_cast<uint8_t*>(s.out.p);
+    d.digests = static_cast<uint8_t*>(s.dig.p);
+    d.corrupt = static_cast<uint8_t*>(s.flags.p);
+    return c->eng->launch_fused(d, c->opt, s.st);
+  }
   for (int pass = 0; pass < 2; pass++) {
     const int64_t first = pass == 0 ? 0 : nfull;
     const int64_t nb = pass == 0 ? nfull : ch.nb - nfull;

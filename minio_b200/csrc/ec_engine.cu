@@ -582,6 +582,7 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       p.in_shard_step = d.contiguous ? d.S : 0;
       p.block_len = d.block_len;
       p.blocks = d.blocks;
+      p.tail_block = d.tail_block; p.tail_in_off = d.tail_in_off; p.tail_S = d.tail_S; p.tail_bytes = d.tail_bytes;
       const int gw = small_gf_warps(n);
       const SmallFn sfn = se ? se->small : kDynSmall[gw - 3][d.r <= 1 ? 0 : (d.r == 2 ? 1 : 2)];
       const void* kfn = reinterpret_cast<const void*>(sfn);
@@ -600,7 +601,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
     }
   }
 
-  if (d.block_len != nullptr || d.blocks != nullptr) return MEC_ERR_UNSUPPORTED;  // per-block geometry exists in the latency kernel only
+  if (d.block_len != nullptr || d.blocks != nullptr || d.tail_block >= 0) return MEC_ERR_UNSUPPORTED;  // per-block geometry exists in the latency kernel only
+  p.tail_block = -1;
 
   // ---- input addressing + loader choice.  TMA boxes must start on 16-byte boundaries, so each row is
   // fetched from the aligned-down address and the kernel skips in_align[t] bytes.

@@ -79,6 +79,10 @@ struct FusedParams {
   uint32_t* work_counter;          // optional: groups beyond the first of every CTA are claimed from this counter (zeroed per launch)
   const int32_t* block_len;        // latency kernel only: shard bytes of every erasure block (nullptr: S for all) — frames of many files in one launch
   const SmallBlock* blocks;        // latency kernel only, contiguous encode: per-block offset / shard bytes / object bytes (nullptr: uniform)
+  // latency kernel only: ONE block of the launch (an object's short last block) differs from the rest — no table needed
+  int64_t tail_block;              // its index, -1 = none
+  int64_t tail_in_off;             // contiguous encode: bytes from in_ptr[0] to its first byte (rows S_tail apart); -1: rows addressed like the others
+  int32_t tail_S, tail_bytes;      // its shard bytes; contiguous encode: its object bytes
 };
 
 // ------------------------------------------------------------------ GF policies

@@ -69,7 +69,8 @@ __global__ void __launch_bounds__(256, 2) small_rs_hh_kernel(const __grid_consta
 
   const int64_t b = blockIdx.x;
   // per-block geometry: the short last frames of many part files, or the blocks of many PutObjects, ride in one launch
-  const int32_t S = p.blocks != nullptr ? p.blocks[b].S : (p.block_len != nullptr ? p.block_len[b] : p.S);
+  const bool is_tail = p.tail_block == b;
+  const int32_t S = p.blocks != nullptr ? p.blocks[b].S : (p.block_len != nullptr ? p.block_len[b] : (is_tail ? p.tail_S : p.S));
   const int nst = (S + kSmallSuper - 1) / kSmallSuper;
 
   if (tid == 0) {
@@ -85,6 +86,9 @@ __global__ void __launch_bounds__(256, 2) small_rs_hh_kernel(const __grid_consta
     if (p.blocks != nullptr) {
       a = p.in_ptr[0] + p.blocks[b].in_off + static_cast<int64_t>(tid) * S;
       valid = static_cast<int64_t>(p.blocks[b].bytes) - static_cast<int64_t>(tid) * S;
+    } else if (is_tail && p.tail_in_off >= 0) {
+      a = p.in_ptr[0] + p.tail_in_off + static_cast<int64_t>(tid) * S;
+      valid = static_cast<int64_t>(p.tail_bytes) - static_cast<int64_t>(tid) * S;
     }
     valid = valid < 0 ? 0 : (valid > S ? S : valid);
     SmallRow rw;

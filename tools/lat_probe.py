@@ -16,8 +16,8 @@ from minio_b200 import capi
 def main():
     k, m, bs = 12, 4, 1 << 20
     L = capi.lib()
-    for size_mib in (1, 4, 16):
-        size = size_mib << 20
+    for size_mib in (1, 1.5, 4, 16):
+        size = int(size_mib * (1 << 20)) + (4321 if size_mib != int(size_mib) else 0)
         for small in (-1, 0):
             c = mb.Codec(k, m, bs)
             c.set_option("small_blocks", small)
