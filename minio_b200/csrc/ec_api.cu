@@ -2468,9 +2468,12 @@ static void batcher_main(mec_batcher* b) {
       if (b->stop && b->queue.empty() && nbusy == 0) return;
       if (!b->queue.empty() && nbusy < kSlots) {
         // gather: whatever is queued now; when nothing is in flight, give concurrent callers max_wait_us to join
+        auto req_blocks = [&](const BatchReq* r) -> int64_t {
+          return r->kind == 0 ? ceil_frac(r->len, c->block_size) : (r->length / c->block_size + 2);
+        };
         auto blocks_queued = [&] {
           int64_t nb = 0;
-          for (BatchReq* r : b->queue) nb += ceil_frac(r->len, c->block_size);
+          for (BatchReq* r : b->queue) nb += req_blocks(r);
           return nb;
         };
         // an idle GPU gives the first caller up to max_wait_us of company before its batch is cut
@@ -2492,7 +2495,7 @@ static void batcher_main(mec_batcher* b) {
         for (auto it = b->queue.begin(); it != b->queue.end();) {
           BatchReq* r = *it;
           if (r->kind != lead->kind || (r->kind == 1 && r->alive_mask != lead->alive_mask)) { ++it; continue; }
-          const int64_t rb = r->kind == 0 ? ceil_frac(r->len, c->block_size) : (r->length / c->block_size + 2);
+          const int64_t rb = req_blocks(r);
           if (!reqs.empty() && nb + rb > cap) break;
           reqs.push_back(r);
           it = b->queue.erase(it);
