@@ -609,6 +609,8 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
   const int64_t ntiles = (static_cast<int64_t>(d.S) + kTile - 1) / kTile;
   bool use_tma = !opt.force_bytewise && d.S > 0;
   bool any_misaligned = false, rows3d = false, direct = false;
+  void* jit3d = nullptr;      // NVRTC-specialised encode kernel with the one-request-per-tile fetch, when it is ready
+  bool jit3d_tried = false;
   p.in_block_stride = d.in_block_stride;
   p.raw_pitch = kRawRow;
   if (d.contiguous) {
@@ -633,12 +635,21 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       // 3-D fetch mode (compile-time specialised encode only): rows at the uniform stride S & ~15
       const int sm16 = static_cast<int>(d.S & 15);
       const int64_t row_stride = static_cast<int64_t>(d.S) & ~15ll;
-      if (se && !opt.no_rows3d && eb == kStaticEb && sm16 == se->sm16 && d.in_block_len == d.in_block_stride &&
-          !(opt.use_auto == 1 && se->aligned_auto && sm16 == 0)) {
+      // ... and, since round 2, the encode of a geometry without a compiled kernel once NVRTC has specialised it (same template,
+      // ALIGN = S mod 16 and the matrix baked in): asked for here, because the tensor maps below depend on which kernel will run
+      const bool jit_enc = !se && d.hash_outputs && d.r >= 1 && !opt.force_dynamic && opt.jit != 0;
+      if ((se || jit_enc) && !opt.no_rows3d && eb == kStaticEb && (!se || sm16 == se->sm16) && d.in_block_len == d.in_block_stride &&
+          !(se && opt.use_auto == 1 && se->aligned_auto && sm16 == 0)) {
         const int rg = direct ? d.k : rows_per_request_3d(d.k, sm16, eb);  // shard rows per request (ec_kernel.cuh)
         const int raw3 = direct ? kRowPitch : raw_row_3d(d.k, sm16, eb, rg);
         const int shift_max = group_shift_3d((d.k - 1) / rg, sm16, rg);
-        if (row_stride >= raw3 + shift_max) {
+        bool kernel_ready = se != nullptr;
+        if (!se && row_stride >= raw3 + shift_max) {
+          jit3d_tried = true;
+          jit3d = jit_kernel(d.k, d.r, d.coef, sm16, kStaticEb, true, true, opt.jit == 1 ? 1 : -1, d.nblocks * static_cast<int64_t>(d.S) * d.k);
+          kernel_ready = jit3d != nullptr;
+        }
+        if (kernel_ready && row_stride >= raw3 + shift_max) {
           CUtensorMap m3;
           if (make_map(encode_tiled_, &m3, d.in_base, static_cast<uint64_t>(row_stride / 4), static_cast<uint64_t>(d.nblocks), stride,
                        static_cast<uint32_t>(raw3 / 4), static_cast<uint32_t>(eb), static_cast<uint64_t>(d.k),
@@ -752,8 +763,10 @@ int Engine::launch_fused(const FusedDesc& d, const EngineOptions& opt, cudaStrea
       void* jk = nullptr;
       if (!d.contiguous && !any_misaligned)  // decode rows, aligned staging
         jk = jit_kernel(d.k, d.r, d.coef, 0, eb == kStaticEb ? kStaticEb : 0, false, d.hash_outputs, mode, in_bytes);
-      else if (d.contiguous && d.hash_outputs && eb == kStaticEb)  // any (k, m) encode
-        jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false, true, mode, in_bytes);
+      else if (d.contiguous && d.hash_outputs && eb == kStaticEb) {  // any (k, m) encode
+        if (jit3d_tried) jk = rows3d ? jit3d : nullptr;  // the 3-D variant is the one being compiled for this geometry
+        else jk = jit_kernel(d.k, d.r, d.coef, static_cast<int>(d.S & 15), kStaticEb, false, true, mode, in_bytes);
+      }
       if (jk) { kfn = jk; jitted = true; }
     }
   }

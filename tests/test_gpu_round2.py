@@ -632,3 +632,24 @@ def test_split_padding_is_zero_over_stale_staging(mb, oracle):
         assert hint == 0 and np.array_equal(out, d), size
         c.encode(np.full(3 * MiB, 0xFF, dtype=np.uint8))            # dirty the staging again
     c.close()
+
+
+@pytest.mark.parametrize("k,m", [(10, 4), (7, 5), (6, 3), (8, 2)])
+def test_nvrtc_specialised_encode_fetches_tiles_with_one_request(mb, oracle, k, m):
+    """Geometries without a compiled kernel: with jit = 1 the encode runs the NVRTC-specialised kernel, which since round 2 uses the
+    one-3-D-TMA-request-per-tile fetch of the compiled ones (S mod 16 = 10, 5, 11, 0 here).  Frames equal the oracle's for whole and
+    ragged objects; the option no_rows3d selects the row-by-row fetch of the same specialisation."""
+    bs = MiB
+    for rows3d_off in (0, 1):
+        c = mb.Codec(k, m, bs)
+        c.set_option("jit", 1)
+        c.set_option("eb", 4)   # the CTA shape of the specialised kernels, also for launches this small (the default would shrink it)
+        c.set_option("no_rows3d", rows3d_off)
+        for size in (8 * MiB, 12 * MiB + 777, 4 * MiB - 5):   # host pipeline chunks of four blocks: 2 + 3 specialised launches, the rest generic
+            d = rand(size, 600 + k + size % 13)
+            files = c.encode(d)
+            want, _ = oracle.erasure_encode(k, m, bs, oracle.HIGHWAYHASH256S, d)
+            for i in range(k + m):
+                assert np.array_equal(files[i], want[i]), (k, m, size, i, rows3d_off)
+        assert c.stat("jit_launches") >= 3
+        c.close()

@@ -266,6 +266,8 @@ if __name__ == "__main__":
         for _ in range(3):
             jit_encode_case(10, 4, MiB, 4096)
         jit_encode_case(10, 4, MiB, 8192)
+        jit_encode_case(7, 5, MiB, 4096)
+        jit_encode_case(6, 3, MiB, 4096)
         sys.exit(0)
     if only == "4k":   # one case, e.g. under ncu
         reconstruct_case("4: RS(16,4) heal shape, stale {0,7,16,19}", 16, 4, MiB, int(sys.argv[2]) if len(sys.argv) > 2 else 2960, {0, 7, 16, 19}, 4, 0)
